@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- path-contexts/sec of the code2vec path-attention forward on B200.
+
+Metric (BASELINE.json): path-contexts/sec = batch x bag x steps / seconds, every slot valid,
+plus the fused-kernel HBM GB/s against the measured roofline.
+
+A "step" is one Code2Vec.forward (fused gather+encode+attention kernel, per-bag finalize,
+label logits, argmax) over one batch of 1024 synthetic bags of 200 contexts.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
+    python bench.py --impl reference [...]                          # the reference's CPU path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Our arm prints ONE JSON line with `value` (inputs resident in HBM), `e2e` (host buffers through
+the C-ABI c2v_forward_host, H2D/D2H inside the timed region), `roofline` (dominant kernel timed
+with CUDA events on its stream), `cpu_baseline` (the oracle's torch-CPU restatement on a bounded
+sample, rank 0, N=1 only), `clocks`, `gpu_launches`.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (single GPU)
+    "cfg2": dict(T=360633, P=342846, C=8192, Et=128, Ep=128, H=128, B=1024, L=200,
+                 desc="synthetic methods x 200 contexts, embed=128/128, encode=128, batch=1024 "
+                      "(top11-sized vocab: T=360,633 P=342,846; C=8,192)"),
+    # configs[4]: large-vocab stress (gather-bound)
+    "cfg5": dict(T=2000000, P=500000, C=8192, Et=128, Ep=128, H=128, B=1024, L=200,
+                 desc="large-vocab stress: 2M terminals / 500K paths, embed=128, encode=128, batch=1024"),
+    # small variant for quick functional runs
+    "tiny": dict(T=5000, P=4000, C=256, Et=128, Ep=128, H=128, B=64, L=200, desc="tiny functional run"),
+}
+
+
+def bytes_per_ctx(w):
+    """3 int64 indices + three fp32 rows per context, + per-bag outputs."""
+    D = 2 * w["Et"] + w["Ep"]
+    return 24 + 4 * D + (4 * w["H"] + 4 * w["L"]) / w["L"]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            j = json.load(open(path))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_params(w, device, seed=1):
+    """Random-init weights of the reference architecture (model.py:18-42 init distributions)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    D = 2 * w["Et"] + w["Ep"]
+    r = lambda *s: torch.randn(*s, generator=g, device=device, dtype=torch.float32)
+    u = lambda bound, *s: (torch.rand(*s, generator=g, device=device, dtype=torch.float32) * 2 - 1) * bound
+    return {
+        "terminal_embedding.weight": r(w["T"], w["Et"]), "path_embedding.weight": r(w["P"], w["Ep"]),
+        "input_linear.weight": u(D ** -0.5, w["H"], D),
+        "input_layer_norm.weight": torch.ones(w["H"], device=device), "input_layer_norm.bias": torch.zeros(w["H"], device=device),
+        "attention_parameter": r(w["H"]) * (2.0 / (w["H"] + 1)) ** 0.5,
+        "output_linear.weight": u(w["H"] ** -0.5, w["C"], w["H"]), "output_linear.bias": torch.zeros(w["C"], device=device),
+    }
+
+
+def synth_pool(w, n_batches, device, seed):
+    """Device-resident index pool: every slot valid, uniform over the vocab."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    n = n_batches * w["B"]
+    mk = lambda hi: torch.randint(1, hi, (n, w["L"]), generator=g, device=device, dtype=torch.int64)
+    return mk(w["T"]), mk(w["P"]), mk(w["T"]), torch.randint(0, w["C"], (n,), generator=g, device=device, dtype=torch.int64)
+
+
+def run_reference(args, w):
+    """The reference's own CPU implementation of the path, timed on this box's host cores.
+    The reference is pure PyTorch and cannot travel to the GPU box (no pip-installable package,
+    /root/reference absent there), so this runs oracle.torch_forward: the same ATen CPU ops
+    in the same order (pinned to the reference by tests/test_oracle_golden.py)."""
+    import torch
+    from oracle import oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    dev = torch.device("cpu")
+    p = synth_params(w, dev)
+    s, pth, e, lab = synth_pool(w, 2, dev, 1234)
+    B, L = w["B"], w["L"]
+
+    def step(i):
+        o = (i % 2) * B
+        with torch.no_grad():
+            out, cv, att = oracle.torch_forward(p, s[o:o + B], pth[o:o + B], e[o:o + B], lab[o:o + B])
+            return out.max(dim=1)
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    val = B * L * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "path-contexts/sec", "value": val, "unit": "ctx/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "detail": w["desc"], "batch": B, "bag": L},
+        "cpu_baseline": {"value": val, "unit": "ctx/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} forward passes of one {B}x{L} batch, torch-CPU restatement "
+                                   f"(oracle.torch_forward), {torch.get_num_threads()} threads"},
+        "e2e": {"value": val, "unit": "ctx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", default="auto", choices=["auto", "ffma", "tcgen05"])
+    ap.add_argument("--pool-batches", type=int, default=64, help="distinct batches in the device index pool")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload]); w["name"] = args.workload
+
+    if args.impl == "reference":
+        if args.steps == 200:
+            args.steps = 20
+        return run_reference(args, w)
+
+    import numpy as np
+    import torch
+    from code2vec_b200 import _lib
+    from code2vec_b200 import functional as CF
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    algo = {"auto": _lib.ALGO_AUTO, "ffma": _lib.ALGO_FFMA, "tcgen05": _lib.ALGO_TCGEN05}[args.algo]
+
+    B, L, H, C = w["B"], w["L"], w["H"], w["C"]
+    dims = CF.make_dims(w["T"], w["P"], C, w["Et"], w["Ep"], H)
+    p = synth_params(w, dev)                        # same weights on every rank (replicated parameters)
+    params = CF.make_params(p["terminal_embedding.weight"], p["path_embedding.weight"], p["input_linear.weight"],
+                            p["input_layer_norm.weight"], p["input_layer_norm.bias"], p["attention_parameter"],
+                            p["output_linear.weight"], p["output_linear.bias"])
+    s, pth, e, lab = synth_pool(w, args.pool_batches, dev, 1234 + rank)   # each rank: its own shard of methods
+    nb = args.pool_batches
+
+    # preallocated outputs / workspaces: the timed region launches kernels only
+    cv = torch.empty((B, H), dtype=torch.float32, device=dev)
+    att = torch.empty((B, L), dtype=torch.float32, device=dev)
+    out = torch.empty((B, C), dtype=torch.float32, device=dev)
+    am = torch.empty((B,), dtype=torch.int64, device=dev); mx = torch.empty((B,), dtype=torch.float32, device=dev)
+    ws_n = lib.c2v_encode_workspace_bytes(ctypes.byref(dims), B, L)
+    ws = torch.empty((ws_n,), dtype=torch.uint8, device=dev)
+    wl_n = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
+    wl = torch.empty((wl_n,), dtype=torch.uint8, device=dev)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    stream = torch.cuda.current_stream(dev)
+    st = ctypes.c_void_p(stream.cuda_stream)
+    label_algo = _lib.ALGO_FFMA if algo == _lib.ALGO_FFMA else _lib.ALGO_AUTO
+
+    def step(i):
+        o = (i % nb) * B
+        _lib.check(lib.c2v_encode_forward(ctypes.byref(dims), ctypes.byref(params), P(s[o:o + B]), P(pth[o:o + B]),
+                                          P(e[o:o + B]), B, L, None, P(cv), P(att), P(ws), ws_n, algo, st), "encode")
+        _lib.check(lib.c2v_label_logits(ctypes.byref(dims), ctypes.byref(params), P(cv), B, P(out), P(wl), wl_n,
+                                        label_algo, st), "label")
+        _lib.check(lib.c2v_loss_argmax(P(out), None, B, C, None, P(am), P(mx), None, st), "argmax")
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- parity gate on the first batch (rank 0): CUDA vs the CPU oracle restatement ----------
+    parity = None
+    if rank == 0:
+        from oracle import oracle
+        step(0); torch.cuda.synchronize(dev)
+        nchk = min(B, 64)
+        cp = {k: v.cpu() for k, v in p.items()}
+        with torch.no_grad():
+            ro, rc_, ra = oracle.torch_forward(cp, s[:nchk].cpu(), pth[:nchk].cpu(), e[:nchk].cpu(), lab[:nchk].cpu())
+        parity = {"max_abs_err": {"outputs": float((out[:nchk].cpu() - ro).abs().max()),
+                                  "code_vector": float((cv[:nchk].cpu() - rc_).abs().max()),
+                                  "attention": float((att[:nchk].cpu() - ra).abs().max())},
+                  "bags_checked": nchk, "tolerance": 1e-4}
+        parity["ok"] = max(parity["max_abs_err"].values()) <= 1e-4
+
+    # ---- device-resident throughput ("value") --------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.c2v_profile_enable(1)
+    l0 = lib.c2v_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.c2v_launch_count() - l0
+    kms, kcnt = ctypes.c_double(0), ctypes.c_int64(0)
+    lib.c2v_profile_read(ctypes.byref(kms), ctypes.byref(kcnt))
+    lib.c2v_profile_enable(0)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    value = world * B * L * args.steps / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (this rank) -----------------------------------------------
+    peak, peak_src = measured_peaks()
+    k_ms = kms.value / max(1, kcnt.value)
+    alg_bytes = bytes_per_ctx(w) * B * L
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "encode_tcgen05_kernel" if lib.c2v_encode_supports_tcgen05(ctypes.byref(dims)) and algo != _lib.ALGO_FFMA else "encode_ffma_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "ctx_per_s_kernel_only": B * L / (k_ms * 1e-3) if k_ms > 0 else 0.0}
+
+    # ---- end to end through the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside) ------
+    e2e = None
+    if not args.no_e2e:
+        sess = ctypes.c_void_p()
+        _lib.check(lib.c2v_session_create(local, ctypes.byref(dims), B, L, ctypes.byref(sess)), "session")
+        hb = min(nb, 8)
+        hs, hp, he = s[:hb * B].cpu().pin_memory(), pth[:hb * B].cpu().pin_memory(), e[:hb * B].cpu().pin_memory()
+        hcv = [torch.empty((B, H), dtype=torch.float32).pin_memory() for _ in range(2)]
+        hat = [torch.empty((B, L), dtype=torch.float32).pin_memory() for _ in range(2)]
+        hpr = [torch.empty((B,), dtype=torch.int64).pin_memory() for _ in range(2)]
+        hsc = [torch.empty((B,), dtype=torch.float32).pin_memory() for _ in range(2)]
+        tick = ctypes.c_int64(0)
+
+        def host_loop(n):
+            pending = []
+            for i in range(n):
+                o = (i % hb) * B; k = i & 1
+                _lib.check(lib.c2v_forward_host_async(sess, ctypes.byref(params), P(hs[o:o + B]), P(hp[o:o + B]),
+                                                      P(he[o:o + B]), None, B, None, P(hcv[k]), P(hat[k]), P(hpr[k]),
+                                                      P(hsc[k]), algo, ctypes.byref(tick)), "forward_host_async")
+                pending.append(tick.value)
+                if len(pending) == 2:       # results of step i-1 are consumed while step i is in flight
+                    _lib.check(lib.c2v_session_wait(sess, pending.pop(0)), "session_wait")
+            for tk in pending:
+                _lib.check(lib.c2v_session_wait(sess, tk), "session_wait")
+        host_loop(max(args.warmup, 3))
+        barrier()
+        t0 = time.perf_counter()
+        host_loop(args.steps)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        lib.c2v_session_destroy(sess)
+        e2e = {"value": world * B * L * args.steps / float(te.item()), "unit": "ctx/s",
+               "h2d_bytes_per_step": 3 * B * L * 8, "d2h_bytes_per_step": B * H * 4 + B * L * 4 + B * 8 + B * 4 + 8,
+               "api": "c2v_forward_host_async (double-buffered; pinned host int64 indices in, code_vector + "
+                      "attention + argmax/score out)", "ms_per_step": float(te.item()) / args.steps * 1e3}
+
+    # ---- CPU baseline beside it: rank 0, N=1 only, bounded sample ------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cp = {k: v.cpu() for k, v in p.items()}
+        cs, cpth, ce, cl = s[:B].cpu(), pth[:B].cpu(), e[:B].cpu(), lab[:B].cpu()
+        with torch.no_grad():
+            for _ in range(2):
+                oracle.torch_forward(cp, cs, cpth, ce, cl)
+            n_it, t0 = 0, time.perf_counter()
+            while n_it < 5 or (time.perf_counter() - t0 < 10.0 and n_it < 200):
+                oracle.torch_forward(cp, cs, cpth, ce, cl)[0].max(dim=1)
+                n_it += 1
+            dt = time.perf_counter() - t0
+        cpu = {"value": B * L * n_it / dt, "unit": "ctx/s", "cores": cores, "kind": "port",
+               "sample": f"{n_it} forward passes of the first {B}x{L} batch of this workload, same weights, "
+                         f"torch-CPU restatement of model.py:44-105 (oracle.torch_forward), {cores} threads",
+               "ms_per_batch": dt / n_it * 1e3}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "path-contexts/sec", "value": value, "unit": "ctx/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "detail": w["desc"], "batch_per_gpu": B, "bag": L,
+                       "step": "Code2Vec.forward: encode + finalize + label logits + argmax",
+                       "algo": args.algo, "sharding": "methods sharded by rank, parameters replicated, no collective in forward",
+                       "l2": f"inputs larger than L2: {(w['T'] * w['Et'] + w['P'] * w['Ep']) * 4 / 1e6:.0f} MB of tables, "
+                             f"{nb} distinct batches ({nb * B * L * 24 / 1e6:.0f} MB of indices) cycled"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(lt.item()), "parity": parity,
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

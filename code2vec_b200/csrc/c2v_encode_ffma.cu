@@ -1,0 +1,338 @@
+// c2v_encode_ffma.cu -- any-shape fp32 CUDA-core encode path + the per-bag finalize.
+//
+// Replaces model.py:48-69 and get_attention (model.py:90-96) of the reference with
+//   K1a encode_ffma_kernel : gathers + concat + input_linear + LayerNorm + tanh (+dropout)
+//                            + masked score + per-(tile,bag) online-softmax partials
+//   K1f encode_finalize    : merges the partials of each bag -> code_vector, attention
+// The [N, D] concat, the [N, H] activations and both expanded products of the eager
+// pipeline are never written to HBM.
+//
+// This is the fallback for shapes the tcgen05 kernel does not take; it is FFMA-bound
+// (<= ~15 % of the HBM roofline at E=H=128).
+#include "c2v_common.cuh"
+
+namespace c2v {
+
+// ------------------------------------------------------------------------------------
+// W [H, D] -> W^T [D][Hs] so the k-chunks of the B operand are coalesced 16-B copies.
+// ------------------------------------------------------------------------------------
+__global__ void transpose_w_kernel(const float *__restrict__ W, float *__restrict__ Wt, int H,
+                                   int D, int Hs)
+{
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int h = h0 + i, k = k0 + threadIdx.x;
+        tile[i][threadIdx.x] = (h < H && k < D) ? W[(size_t)h * D + k] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int k = k0 + i, h = h0 + threadIdx.x;
+        if (k < D && h < Hs) Wt[(size_t)k * Hs + h] = tile[threadIdx.x][i];
+    }
+}
+
+int launch_transpose_w(const float *W, float *Wt, int H, int D, int Hs, cudaStream_t st)
+{
+    dim3 grid((D + 31) / 32, (Hs + 31) / 32), block(32, 8);
+    transpose_w_kernel<<<grid, block, 0, st>>>(W, Wt, H, D, Hs);
+    C2V_LAUNCH_OK("transpose_w_kernel");
+    return C2V_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// K1a
+// ------------------------------------------------------------------------------------
+constexpr int TM = 64;        // context rows per tile
+constexpr int KC = 32;        // k-chunk
+constexpr int KCP = KC + 4;   // padded A row (keeps 16-B alignment)
+constexpr int NB = 128;       // output columns per column block
+constexpr int THREADS = 256;
+
+struct FfmaSmem {
+    // byte offsets into dynamic smem
+    int idx, ac, wc, x, z, e, m, total;
+};
+__host__ __device__ inline FfmaSmem ffma_smem_layout(int Hs)
+{
+    FfmaSmem s;
+    int o = 0;
+    s.idx = o; o += 3 * TM * 8;
+    s.ac = o;  o += 2 * TM * KCP * 4;
+    s.wc = o;  o += 2 * KC * NB * 4;
+    s.x = o;   o += TM * Hs * 4;
+    s.z = o;   o += TM * 4;
+    s.e = o;   o += TM * 4;
+    s.m = o;   o += TM * 4;
+    s.total = o;
+    return s;
+}
+
+template <bool VEC>
+__device__ __forceinline__ void load_a_chunk(const EncodeArgs &a, const long long *sidx, float *Ac,
+                                             int kc)
+{
+    // TM rows x KC floats of the concatenated context vector [start ; path ; end] (model.py:51)
+    const int D = a.D, Et = a.Et, Ep = a.Ep;
+    if (VEC) {
+        for (int i = threadIdx.x; i < TM * (KC / 4); i += THREADS) {
+            const int r = i / (KC / 4), kq = i % (KC / 4);
+            const int k = kc * KC + kq * 4;
+            float *dst = Ac + r * KCP + kq * 4;
+            if (k < D) {
+                const float *src;
+                if (k < Et) src = a.emb_t + (size_t)sidx[r] * Et + k;
+                else if (k < Et + Ep) src = a.emb_p + (size_t)sidx[TM + r] * Ep + (k - Et);
+                else src = a.emb_t + (size_t)sidx[2 * TM + r] * Et + (k - Et - Ep);
+                cp_async16(dst, src);
+            } else {
+                *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < TM * KC; i += THREADS) {
+            const int r = i / KC, kk = i % KC;
+            const int k = kc * KC + kk;
+            float *dst = Ac + r * KCP + kk;
+            if (k < D) {
+                const float *src;
+                if (k < Et) src = a.emb_t + (size_t)sidx[r] * Et + k;
+                else if (k < Et + Ep) src = a.emb_p + (size_t)sidx[TM + r] * Ep + (k - Et);
+                else src = a.emb_t + (size_t)sidx[2 * TM + r] * Et + (k - Et - Ep);
+                cp_async4(dst, src);
+            } else {
+                *dst = 0.0f;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void load_w_chunk(const float *__restrict__ Wt, int D, int Hs, float *Wc,
+                                             int kc, int cb)
+{
+    for (int i = threadIdx.x; i < KC * (NB / 4); i += THREADS) {
+        const int kk = i / (NB / 4), cq = i % (NB / 4);
+        const int k = kc * KC + kk, col = cb * NB + cq * 4;
+        float *dst = Wc + kk * NB + cq * 4;
+        if (k < D && col < Hs) cp_async16(dst, Wt + (size_t)k * Hs + col);
+        else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(THREADS)
+encode_ffma_kernel(const EncodeArgs a, const int Hs)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const FfmaSmem lay = ffma_smem_layout(Hs);
+    long long *sidx = reinterpret_cast<long long *>(smem + lay.idx);
+    float *Ac = reinterpret_cast<float *>(smem + lay.ac);
+    float *Wc = reinterpret_cast<float *>(smem + lay.wc);
+    float *X = reinterpret_cast<float *>(smem + lay.x);
+    float *zbuf = reinterpret_cast<float *>(smem + lay.z);
+    float *ebuf = reinterpret_cast<float *>(smem + lay.e);
+    float *mbuf = reinterpret_cast<float *>(smem + lay.m);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int H = a.H, D = a.D, L = a.L;
+    const int n_kc = (D + KC - 1) / KC;
+    const int n_cb = (H + NB - 1) / NB;
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const long long row0 = (long long)tile * TM;
+        // ---- indices of this tile (model.py:48-50); bad ones are clamped to row 0 and counted
+        for (int i = tid; i < 3 * TM; i += THREADS) {
+            const int which = i / TM, r = i % TM;
+            const long long row = row0 + r;
+            long long v = 0;
+            if (row < a.N) {
+                const long long *src = which == 0 ? a.starts : which == 1 ? a.paths : a.ends;
+                v = src[row];
+                const long long lim = which == 1 ? a.P : a.T;
+                if (v < 0 || v >= lim) { atomicAdd((unsigned long long *)a.ws.status, 1ull); v = 0; }
+            }
+            sidx[i] = v;
+        }
+        __syncthreads();
+
+        // ---- x = c . W^T (model.py:54), one 128-column block at a time -----------------
+        for (int cb = 0; cb < n_cb; ++cb) {
+            float acc[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+            load_a_chunk<VEC>(a, sidx, Ac, 0);
+            load_w_chunk(a.ws.w_t, D, Hs, Wc, 0, cb);
+            cp_async_commit();
+            for (int kc = 0; kc < n_kc; ++kc) {
+                const int buf = kc & 1;
+                if (kc + 1 < n_kc) {
+                    load_a_chunk<VEC>(a, sidx, Ac + (buf ^ 1) * TM * KCP, kc + 1);
+                    load_w_chunk(a.ws.w_t, D, Hs, Wc + (buf ^ 1) * KC * NB, kc + 1, cb);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
+                const float *Ab = Ac + buf * TM * KCP + (ty * 4) * KCP;
+                const float *Wb = Wc + buf * KC * NB;
+#pragma unroll
+                for (int k4 = 0; k4 < KC; k4 += 4) {
+                    float4 av[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4 *>(Ab + i * KCP + k4);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float4 w0 = *reinterpret_cast<const float4 *>(Wb + (k4 + kk) * NB + tx * 4);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(Wb + (k4 + kk) * NB + 64 + tx * 4);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float ai = kk == 0 ? av[i].x : kk == 1 ? av[i].y : kk == 2 ? av[i].z : av[i].w;
+                            acc[i][0] = fmaf(ai, w0.x, acc[i][0]); acc[i][1] = fmaf(ai, w0.y, acc[i][1]);
+                            acc[i][2] = fmaf(ai, w0.z, acc[i][2]); acc[i][3] = fmaf(ai, w0.w, acc[i][3]);
+                            acc[i][4] = fmaf(ai, w1.x, acc[i][4]); acc[i][5] = fmaf(ai, w1.y, acc[i][5]);
+                            acc[i][6] = fmaf(ai, w1.z, acc[i][6]); acc[i][7] = fmaf(ai, w1.w, acc[i][7]);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = ty * 4 + i;
+                const int c0 = cb * NB + tx * 4, c1 = c0 + 64;
+                if (c0 < Hs) *reinterpret_cast<float4 *>(X + r * Hs + c0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                if (c1 < Hs) *reinterpret_cast<float4 *>(X + r * Hs + c1) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+            }
+        }
+        __syncthreads();
+
+        // ---- LayerNorm + tanh (+dropout) + score, one warp per row (model.py:55-61, 92-93)
+        for (int r = warp; r < TM; r += THREADS / 32) {
+            const long long row = row0 + r;
+            float *xr = X + r * Hs;
+            float s = 0.0f;
+            for (int c = lane; c < H; c += 32) s += xr[c];
+            const float mean = warp_sum(s) / (float)H;
+            float v = 0.0f;
+            for (int c = lane; c < H; c += 32) { const float d = xr[c] - mean; v = fmaf(d, d, v); }
+            const float rstd = 1.0f / sqrtf(warp_sum(v) / (float)H + C2V_LN_EPS);
+            float u = 0.0f;
+            for (int c = lane; c < H; c += 32) {
+                float y = tanh_accurate((xr[c] - mean) * rstd * a.ln_g[c] + a.ln_b[c]);
+                if (a.drop_p > 0.0f) y *= dropout_mask_at(a.seed, row, c, a.drop_p, a.drop_scale);
+                xr[c] = y;
+                u = fmaf(y, a.attn[c], u);
+            }
+            u = warp_sum(u);
+            if (lane == 0) {
+                // model.py:64 mask = starts > 0 ; model.py:93 score*mask + (1-mask)*NINF
+                const float z = (row < a.N && sidx[r] > 0) ? u : C2V_NINF;
+                zbuf[r] = z;
+                if (row < a.N) a.attention[row] = z;
+            }
+        }
+        __syncthreads();
+
+        // ---- per-(tile,bag) segment max and exp weights
+        const int rows_here = (int)((a.N - row0) < TM ? (a.N - row0) : TM);
+        if (tid < rows_here) {
+            const long long row = row0 + tid;
+            const long long bag = row / L;
+            long long lo = bag * L - row0; if (lo < 0) lo = 0;
+            long long hi = (bag + 1) * L - row0; if (hi > rows_here) hi = rows_here;
+            float m = C2V_NINF;
+            for (int q = (int)lo; q < (int)hi; ++q) m = fmaxf(m, zbuf[q]);
+            mbuf[tid] = m;
+            ebuf[tid] = __expf(zbuf[tid] - m);
+        }
+        __syncthreads();
+        const long long bag_first = row0 / L, bag_last = (row0 + rows_here - 1) / L;
+        for (long long bag = bag_first; bag <= bag_last; ++bag) {
+            long long lo = bag * L - row0; if (lo < 0) lo = 0;
+            long long hi = (bag + 1) * L - row0; if (hi > rows_here) hi = rows_here;
+            const size_t slot = (size_t)tile + (size_t)bag;
+            for (int h = tid; h < H; h += THREADS) {
+                float v = 0.0f;
+                for (int q = (int)lo; q < (int)hi; ++q) v = fmaf(ebuf[q], X[q * Hs + h], v);
+                a.ws.part_v[slot * H + h] = v;
+            }
+            if (tid == 0) {
+                float s = 0.0f;
+                for (int q = (int)lo; q < (int)hi; ++q) s += ebuf[q];
+                a.ws.part_m[slot] = mbuf[lo];
+                a.ws.part_s[slot] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int launch_encode_ffma(const EncodeArgs &a, cudaStream_t st)
+{
+    const int Hs = (a.H + 3) / 4 * 4;
+    const FfmaSmem lay = ffma_smem_layout(Hs);
+    const bool vec = (a.Et % 4 == 0) && (a.Ep % 4 == 0);
+    int dev = 0, sms = 0;
+    C2V_CUDA_OK(cudaGetDevice(&dev));
+    C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (lay.total > 227 * 1024) {
+        set_error("encode_ffma: encode_size %d needs %d B of shared memory (> 227 KB)", a.H, lay.total);
+        return C2V_EUNSUPPORTED;
+    }
+    auto kern = vec ? encode_ffma_kernel<true> : encode_ffma_kernel<false>;
+    C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+    int occ = 1;
+    C2V_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, lay.total));
+    if (occ < 1) occ = 1;
+    int grid = a.n_tiles < sms * occ ? a.n_tiles : sms * occ;
+    if (grid < 1) grid = 1;
+    kern<<<grid, THREADS, lay.total, st>>>(a, Hs);
+    C2V_LAUNCH_OK("encode_ffma_kernel");
+    return C2V_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// K1f: merge the (tile, bag) partials of every bag (model.py:96 softmax, :68-69 sum)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+encode_finalize_kernel(const EncodeArgs a, const int tile_rows, float *__restrict__ code_vector)
+{
+    const long long bag = blockIdx.x;
+    const int L = a.L, H = a.H;
+    const long long r0 = bag * L;
+    const int t0 = (int)(r0 / tile_rows), t1 = (int)((r0 + L - 1) / tile_rows);
+    float M = C2V_NINF;
+    for (int t = t0; t <= t1; ++t) M = fmaxf(M, a.ws.part_m[(size_t)t + bag]);
+    float S = 0.0f;
+    for (int t = t0; t <= t1; ++t) {
+        const size_t slot = (size_t)t + bag;
+        S += a.ws.part_s[slot] * __expf(a.ws.part_m[slot] - M);
+    }
+    const float inv = 1.0f / S;
+    for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float v = 0.0f;
+        for (int t = t0; t <= t1; ++t) {
+            const size_t slot = (size_t)t + bag;
+            v = fmaf(a.ws.part_v[slot * H + h], __expf(a.ws.part_m[slot] - M), v);
+        }
+        code_vector[bag * H + h] = v * inv;
+    }
+    for (int j = threadIdx.x; j < L; j += blockDim.x) {
+        const float z = a.attention[r0 + j];
+        a.attention[r0 + j] = __expf(z - M) * inv;
+    }
+}
+
+int launch_encode_finalize(const EncodeArgs &a, int B, float *code_vector, cudaStream_t st)
+{
+    encode_finalize_kernel<<<B, 128, 0, st>>>(a, a.ws.tile_rows, code_vector);
+    C2V_LAUNCH_OK("encode_finalize_kernel");
+    return C2V_OK;
+}
+
+}  // namespace c2v

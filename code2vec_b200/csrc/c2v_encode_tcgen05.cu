@@ -1,0 +1,508 @@
+// c2v_encode_tcgen05.cu -- K1b: the fused gather + encode + attention kernel on the
+// 5th-gen tensor cores (sm_100a), for terminal_embed = path_embed = encode = 128.
+//
+// What it replaces: model.py:48-69 + get_attention (model.py:90-96) of the reference.
+//
+// Numerics.  The reference contraction x = c . W^T is fp32; plain TF32/BF16 miss the 1e-4
+// parity bar.  Here both operands are split into fp16 hi + fp16 lo
+// (a = a_hi + a_lo exactly to ~2^-22) and three kind::f16 MMAs with fp32 accumulation are
+// issued per k-step:  a_hi.w_hi + a_lo.w_hi + a_hi.w_lo  (the dropped a_lo.w_lo term is
+// 2^-22 relative).  W is pre-multiplied by a power of two so its lo part stays out of the
+// fp16 subnormals; the epilogue folds the exact inverse into the LayerNorm scale.
+// Measured distance to the reference: ~5e-7 (tests/test_forward_parity_gpu.py).
+//
+// Structure (one persistent CTA per SM, 16 warps, warp-specialised):
+//   warps 0-3   epilogue: TMEM -> registers (one context row per thread), LayerNorm, tanh,
+//               dropout, score, per-warp online-softmax partials (butterfly transpose-reduce)
+//   warps 4-11  A producers: 128-bit coalesced gathers of the fp32 embedding rows, hi/lo fp16
+//               split in registers, st.shared into the UMMA K-major SWIZZLE_128B layout
+//   warp 12     MMA issuer (one elected thread): 12 tcgen05.mma per 64-wide k-block
+//   warp 13     W producer: one 32 KB cp.async.bulk (TMA bulk copy) per k-block of the
+//               pre-split, pre-swizzled weight image
+//   warp 14     TMEM allocator
+// A 3-stage mbarrier ring carries {A_hi, A_lo, W_hi, W_lo} k-blocks (64 KB per stage);
+// two 128-column TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda_fp16.h>
+
+#include "c2v_common.cuh"
+
+namespace c2v {
+
+namespace tc {
+constexpr int ROWS = 128;                 // UMMA M: context rows per tile
+constexpr int E = 128;                    // terminal_embed == path_embed
+constexpr int H = 128;                    // UMMA N: encode size
+constexpr int D = 3 * E;                  // 384
+constexpr int KB = 64;                    // k-block: 64 fp16 = one 128-byte swizzle row
+constexpr int NKB = D / KB;               // 6
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = ROWS * KB * 2; // 16 KB: one [128 x 64] fp16 K-major SW128 tile
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // A_hi | A_lo | W_hi | W_lo
+constexpr int W_KB_BYTES = 2 * TILE_BYTES;    // W_hi | W_lo of one k-block, contiguous in HBM
+constexpr int THREADS = 512;
+constexpr int N_PRODUCER_WARPS = 8;
+constexpr int TMEM_COLS = 256;            // 2 accumulators x 128 fp32 columns
+constexpr int VROWS = 32;                 // rows per partial ("virtual tile" = one epilogue warp)
+// dynamic smem: [<=1023 B align pad][STAGES x 64 KB][gamma|beta|attn 1.5 KB][barriers]
+constexpr int SMEM_VEC_OFF = STAGES * STAGE_BYTES;
+constexpr int SMEM_BAR_OFF = SMEM_VEC_OFF + 3 * H * 4;
+constexpr int SMEM_BYTES = SMEM_BAR_OFF + 128 + 1024;
+// instruction descriptor, kind::f16: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 @17, M>>4 @24
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+}  // namespace tc
+
+bool tcgen05_shape_ok(const c2v_dims *d)
+{
+    return d->terminal_embed == tc::E && d->path_embed == tc::E && d->encode == tc::H;
+}
+
+// ------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spin on the phase parity; a watchdog turns a protocol bug into a trap instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, long long *status) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if ((spins & 0x3ff) == 0x3ff) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000LL) {           // ~2 s: certainly a deadlock
+                status[1] = 0xDEAD0000LL | (long long)(bar & 0xffff);
+                __threadfence();
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B
+// (stride between 8-row groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float4 ldg_nc_v4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+
+// byte offset of fp16 element (row, k) inside a [rows x 64] K-major SWIZZLE_128B tile
+__host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+// In-place transpose-reduce across the 32 lanes of a warp: on entry lane i holds v[0..31]
+// (32 columns of its row); on exit v[0] of lane i is the sum over all 32 lanes of column i.
+// 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ void butterfly_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const float send = upper ? v[j] : v[j + off];
+            const float keep = upper ? v[j + off] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// weight preparation: W [H, D] fp32 -> per k-block {hi tile, lo tile} images in the exact
+// shared-memory layout, scaled by 2^k.  One CTA; 49 K elements.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__restrict__ hdr)
+{
+    __shared__ float red[32];
+    const int tid = threadIdx.x;
+    float mx = 0.0f;
+    for (int i = tid; i < tc::H * tc::D; i += 1024) mx = fmaxf(mx, fabsf(W[i]));
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, red[i]);
+    // largest power of two with max|W| * scale < 2^14 (fp16 max is 65504)
+    float scale = 1.0f;
+    if (mx > 0.0f && mx < 3.0e38f) {
+        int e;
+        frexpf(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
+        int k = 14 - e;
+        k = k > 60 ? 60 : (k < -60 ? -60 : k);
+        scale = ldexpf(1.0f, k);
+    }
+    if (tid == 0) { hdr[0] = 1.0f / scale; hdr[1] = scale; }
+    for (int i = tid; i < tc::H * tc::D; i += 1024) {
+        const int n = i / tc::D, k = i % tc::D;
+        const float w = W[i] * scale;
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn(w - __half2float(hi));
+        const int kb = k / tc::KB, kk = k % tc::KB;
+        uint8_t *base = img + (size_t)kb * tc::W_KB_BYTES;
+        const uint32_t off = sw128_offset(n, kk);
+        *reinterpret_cast<__half *>(base + off) = hi;
+        *reinterpret_cast<__half *>(base + tc::TILE_BYTES + off) = lo;
+    }
+}
+
+int launch_split_w_tcgen05(const c2v_dims *d, const float *W, EncodeWorkspace &ws, cudaStream_t st)
+{
+    (void)d;
+    split_w_kernel<<<1, 1024, 0, st>>>(W, reinterpret_cast<uint8_t *>(ws.w_hi), ws.prep_hdr);
+    C2V_LAUNCH_OK("split_w_kernel");
+    return C2V_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------
+struct ProducerIdx { long long s, p, e; };
+
+__global__ void __launch_bounds__(tc::THREADS, 1)
+encode_tcgen05_kernel(const EncodeArgs a)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B tiles need 1024-B alignment
+    unsigned char *smem = smem_raw + (base - raw);
+    float *s_vec = reinterpret_cast<float *>(smem + tc::SMEM_VEC_OFF);     // gamma | beta | attn
+    const uint32_t bar_base = base + tc::SMEM_BAR_OFF;
+    // barriers (8 B each): full[3] @0, empty[3] @24, tmem_full[2] @48, tmem_empty[2] @64, tmem ptr @80
+    const uint32_t bar_full = bar_base, bar_empty = bar_base + 24, bar_tfull = bar_base + 48,
+                   bar_tempty = bar_base + 64;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + tc::SMEM_BAR_OFF + 80);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    long long *status = a.ws.status;
+
+    if (tid == 0) {
+        for (int s = 0; s < tc::STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, tc::N_PRODUCER_WARPS + 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 14) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)tc::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < 3 * tc::H) {
+        const int which = tid / tc::H, c = tid % tc::H;
+        s_vec[tid] = which == 0 ? a.ln_g[c] : which == 1 ? a.ln_b[c] : a.attn[c];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp < 4) {
+        // =============================== EPILOGUE ===============================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const float inv_scale = a.ws.prep_hdr[0];
+        const float4 *sG = reinterpret_cast<const float4 *>(s_vec);
+        const float4 *sB = reinterpret_cast<const float4 *>(s_vec + tc::H);
+        const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * tc::H);
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+            const int acc = tl & 1;
+            const uint32_t acc_phase = (uint32_t)(tl >> 1) & 1u;
+            const long long vrow0 = (long long)tile * tc::ROWS + warp * tc::VROWS;
+            const long long row = vrow0 + lane;
+            const bool in_range = row < a.N;
+            const long long st_idx = in_range ? a.starts[row] : 0;       // model.py:64 mask = starts > 0
+
+            mbar_wait(bar_tfull + 8 * acc, acc_phase, status);
+            tc_fence_after();
+            float x[tc::H];
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * tc::H);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(taddr + c * 32, x + c * 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);           // accumulator is free again
+
+            // LayerNorm (model.py:55-56), two-pass in registers; x is scale * (c . W^T)
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < tc::H; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
+            const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / tc::H);
+            s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < tc::H; c += 4) {
+                const float d0 = x[c] - mean, d1 = x[c + 1] - mean, d2 = x[c + 2] - mean, d3 = x[c + 3] - mean;
+                s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+            }
+            const float var = ((s0 + s1) + (s2 + s3)) * (1.0f / tc::H) * inv_scale * inv_scale;
+            const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
+            // tanh (model.py:57), dropout (model.py:60-61), score h.a (model.py:92-93)
+            float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < tc::H / 4; ++c4) {
+                const float4 g = sG[c4], b = sB[c4], at = sA[c4];
+                float y0 = tanh_accurate(fmaf((x[4 * c4 + 0] - mean) * nrm, g.x, b.x));
+                float y1 = tanh_accurate(fmaf((x[4 * c4 + 1] - mean) * nrm, g.y, b.y));
+                float y2 = tanh_accurate(fmaf((x[4 * c4 + 2] - mean) * nrm, g.z, b.z));
+                float y3 = tanh_accurate(fmaf((x[4 * c4 + 3] - mean) * nrm, g.w, b.w));
+                if (a.drop_p > 0.0f) {
+                    const uint4 bits = dropout_bits(a.seed, row, c4);
+                    y0 *= dropout_mul(bits.x, a.drop_p, a.drop_scale);
+                    y1 *= dropout_mul(bits.y, a.drop_p, a.drop_scale);
+                    y2 *= dropout_mul(bits.z, a.drop_p, a.drop_scale);
+                    y3 *= dropout_mul(bits.w, a.drop_p, a.drop_scale);
+                }
+                x[4 * c4 + 0] = y0; x[4 * c4 + 1] = y1; x[4 * c4 + 2] = y2; x[4 * c4 + 3] = y3;
+                u0 = fmaf(y0, at.x, u0); u1 = fmaf(y1, at.y, u1);
+                u0 = fmaf(y2, at.z, u0); u1 = fmaf(y3, at.w, u1);
+            }
+            // model.py:93  score*mask + (1-mask)*NINF
+            const float z = (in_range && st_idx > 0) ? (u0 + u1) : C2V_NINF;
+            if (in_range) a.attention[row] = z;
+
+            // per-(warp, bag) online-softmax partial -> slot (vtile + bag)
+            if (vrow0 < a.N) {
+                const long long vt = vrow0 / tc::VROWS;
+                long long last = vrow0 + tc::VROWS - 1; if (last > a.N - 1) last = a.N - 1;
+                const long long bag_lo = vrow0 / a.L, bag_hi = last / a.L;
+                const long long my_bag = row / a.L;
+                for (long long bag = bag_lo; bag <= bag_hi; ++bag) {
+                    const bool in_seg = in_range && my_bag == bag;
+                    const float m = warp_max(in_seg ? z : -INFINITY);
+                    const float e = in_seg ? __expf(z - m) : 0.0f;
+                    const float ssum = warp_sum(e);
+                    const size_t slot = (size_t)(vt + bag);
+                    float *pv = a.ws.part_v + slot * tc::H;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float t[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) t[j] = e * x[c * 32 + j];
+                        butterfly_reduce32(t, lane);
+                        pv[c * 32 + lane] = t[0];
+                    }
+                    if (lane == 0) { a.ws.part_m[slot] = m; a.ws.part_s[slot] = ssum; }
+                }
+            }
+        }
+    } else if (warp < 4 + tc::N_PRODUCER_WARPS) {
+        // =============================== A PRODUCERS ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        const int pw = warp - 4;                     // rows 16*pw .. 16*pw+15 of every tile
+        const int sub_row = lane >> 4;               // which of the 2 rows of a load this lane serves
+        const int q = lane & 15;                     // 16-byte column of the 256-byte half row
+        const int n_items = my_tiles * tc::NKB;
+        const float4 *tab_t = reinterpret_cast<const float4 *>(a.emb_t);
+        const float4 *tab_p = reinterpret_cast<const float4 *>(a.emb_p);
+
+        ProducerIdx raw_next = {0, 0, 0};
+        uint32_t off_s = 0, off_p = 0, off_e = 0;    // row offsets (float4 units) of the tile being loaded
+        auto fetch_idx = [&](int tl) {
+            raw_next.s = raw_next.p = raw_next.e = 0;
+            if (tl < my_tiles) {
+                const long long row = ((long long)blockIdx.x + (long long)tl * gridDim.x) * tc::ROWS + pw * 16 + q;
+                if (row < a.N) { raw_next.s = a.starts[row]; raw_next.p = a.paths[row]; raw_next.e = a.ends[row]; }
+            }
+        };
+        auto adopt_idx = [&]() {
+            long long s = raw_next.s, p = raw_next.p, e = raw_next.e;
+            int bad = 0;
+            if (s < 0 || s >= a.T) { s = 0; ++bad; }
+            if (p < 0 || p >= a.P) { p = 0; ++bad; }
+            if (e < 0 || e >= a.T) { e = 0; ++bad; }
+            if (bad && lane < 16) atomicAdd((unsigned long long *)status, (unsigned long long)bad);
+            off_s = (uint32_t)(s * (tc::E / 4)); off_p = (uint32_t)(p * (tc::E / 4)); off_e = (uint32_t)(e * (tc::E / 4));
+        };
+        auto issue = [&](int it, float4 (&buf)[8]) {
+            const int kb = it % tc::NKB;
+            const int sub = kb >> 1;                                     // 0 start, 1 path, 2 end (model.py:51)
+            const float4 *tab = sub == 1 ? tab_p : tab_t;
+            const uint32_t off = sub == 0 ? off_s : (sub == 1 ? off_p : off_e);
+            const uint32_t col = (uint32_t)((kb & 1) * 16 + q);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t o = __shfl_sync(0xffffffffu, off, 2 * j + sub_row);
+                buf[j] = ldg_nc_v4(tab + (size_t)o + col);
+            }
+        };
+        auto consume = [&](int it, float4 (&buf)[8]) {
+            const int stage = it % tc::STAGES;
+            const uint32_t phase = (uint32_t)(it / tc::STAGES) & 1u;
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1u, status);
+            const uint32_t a_hi = base + stage * tc::STAGE_BYTES, a_lo = a_hi + tc::TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = pw * 16 + 2 * j + sub_row;
+                const float4 v = buf[j];
+                const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y);
+                const __half2 l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+                const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((q >> 1) ^ (r & 7)) & 7) << 4) + (q & 1) * 8);
+                sts_v2(a_hi + off, pack_h2(h01), pack_h2(h23));
+                sts_v2(a_lo + off, pack_h2(l01), pack_h2(l23));
+            }
+            fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+        };
+
+        float4 bufA[8], bufB[8];
+        if (n_items > 0) {
+            fetch_idx(0);
+            adopt_idx();
+            fetch_idx(1);
+            issue(0, bufA);
+            for (int it = 0; it < n_items; it += 2) {
+                if (it + 1 < n_items) {
+                    if ((it + 1) % tc::NKB == 0) { adopt_idx(); fetch_idx((it + 1) / tc::NKB + 1); }
+                    issue(it + 1, bufB);
+                }
+                consume(it, bufA);
+                if (it + 2 < n_items) {
+                    if ((it + 2) % tc::NKB == 0) { adopt_idx(); fetch_idx((it + 2) / tc::NKB + 1); }
+                    issue(it + 2, bufA);
+                }
+                if (it + 1 < n_items) consume(it + 1, bufB);
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 12) {
+            // =============================== MMA ISSUER ===============================
+            if (lane == 0) {
+                for (int tl = 0; tl < my_tiles; ++tl) {
+                    const int acc = tl & 1;
+                    const uint32_t acc_phase = (uint32_t)(tl >> 1) & 1u;
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u, status);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * tc::H);
+                    for (int kb = 0; kb < tc::NKB; ++kb) {
+                        const int it = tl * tc::NKB + kb;
+                        const int stage = it % tc::STAGES;
+                        const uint32_t phase = (uint32_t)(it / tc::STAGES) & 1u;
+                        mbar_wait(bar_full + 8 * stage, phase, status);
+                        tc_fence_after();
+                        const uint32_t sa = base + stage * tc::STAGE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < tc::KB / 16; ++k) {
+                            const uint64_t a_hi = umma_desc(sa + k * 32);
+                            const uint64_t a_lo = umma_desc(sa + tc::TILE_BYTES + k * 32);
+                            const uint64_t w_hi = umma_desc(sa + 2 * tc::TILE_BYTES + k * 32);
+                            const uint64_t w_lo = umma_desc(sa + 3 * tc::TILE_BYTES + k * 32);
+                            umma_f16(d_tmem, a_hi, w_hi, tc::IDESC, (kb | k) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, a_lo, w_hi, tc::IDESC, 1u);
+                            umma_f16(d_tmem, a_hi, w_lo, tc::IDESC, 1u);
+                        }
+                        umma_commit(bar_empty + 8 * stage);       // frees the smem stage when the MMAs retire
+                    }
+                    umma_commit(bar_tfull + 8 * acc);             // accumulator complete -> epilogue
+                }
+            }
+            __syncwarp();
+        } else if (warp == 13) {
+            // =============================== W PRODUCER ===============================
+            if (lane == 0) {
+                const uint8_t *img = reinterpret_cast<const uint8_t *>(a.ws.w_hi);
+                const int n_items = my_tiles * tc::NKB;
+                for (int it = 0; it < n_items; ++it) {
+                    const int stage = it % tc::STAGES;
+                    const uint32_t phase = (uint32_t)(it / tc::STAGES) & 1u;
+                    const int kb = it % tc::NKB;
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1u, status);
+                    mbar_arrive_expect_tx(bar_full + 8 * stage, tc::W_KB_BYTES);
+                    bulk_copy_g2s(base + stage * tc::STAGE_BYTES + 2 * tc::TILE_BYTES,
+                                  img + (size_t)kb * tc::W_KB_BYTES, tc::W_KB_BYTES, bar_full + 8 * stage);
+                }
+            }
+            __syncwarp();
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 14) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tc::TMEM_COLS) : "memory");
+    }
+}
+
+int launch_encode_tcgen05(const EncodeArgs &a, cudaStream_t st)
+{
+    int dev = 0, sms = 0;
+    C2V_CUDA_OK(cudaGetDevice(&dev));
+    C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    C2V_CUDA_OK(cudaFuncSetAttribute(encode_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    int grid = a.n_tiles < sms ? a.n_tiles : sms;
+    if (grid < 1) grid = 1;
+    encode_tcgen05_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a);
+    C2V_LAUNCH_OK("encode_tcgen05_kernel");
+    return C2V_OK;
+}
+
+int launch_label_tcgen05(const c2v_dims *, const float *, int, const float *, const float *, float *,
+                         void *, size_t, cudaStream_t)
+{
+    set_error("tcgen05 label GEMM is not built yet");
+    return C2V_EUNSUPPORTED;
+}
+
+}  // namespace c2v

@@ -1,0 +1,204 @@
+// c2v_head.cu -- label head next to the encode path, CUDA-core versions:
+//   generic strided fp32 GEMM (+bias)            model.py:83 and its backward
+//   angular-margin head                          model.py:71-80
+//   fused log_softmax + NLL + argmax (+dlogits)  main.py:251-264, main.py:285
+#include "c2v_common.cuh"
+
+namespace c2v {
+
+// ------------------------------------------------------------------------------------
+// C[m,n] (+)= sum_k A(m,k) B(k,n) + bias[n] ; 64x64 tile, 16-wide k step, 4x4 per thread.
+// Strides are in elements so NN / NT / TN all map onto it.
+// ------------------------------------------------------------------------------------
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, const float *__restrict__ A, long long a_sm, long long a_sk,
+             const float *__restrict__ B, long long b_sk, long long b_sn,
+             const float *__restrict__ bias, float *__restrict__ C, long long c_sm, int accumulate)
+{
+    __shared__ float As[GK][GT + 4];
+    __shared__ float Bs[GK][GT + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += GK) {
+        for (int i = tid; i < GT * GK; i += 256) {
+            // choose the faster-varying index along the contiguous dimension of each operand
+            int am, ak, bk, bn;
+            if (a_sk == 1) { ak = i % GK; am = i / GK; } else { am = i % GT; ak = i / GT; }
+            if (b_sn == 1) { bn = i % GT; bk = i / GT; } else { bk = i % GK; bn = i / GK; }
+            const int gm = m0 + am, gk = k0 + ak;
+            As[ak][am] = (gm < M && gk < K) ? A[gm * a_sm + gk * a_sk] : 0.0f;
+            const int gn = n0 + bn, gk2 = k0 + bk;
+            Bs[bk][bn] = (gn < N && gk2 < K) ? B[gk2 * b_sk + gn * b_sn] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            const float4 av = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j] + (bias ? bias[gn] : 0.0f);
+            float *dst = C + gm * c_sm + gn;
+            *dst = accumulate ? *dst + v : v;
+        }
+    }
+}
+
+int launch_sgemm(int M, int N, int K, const float *A, long long a_sm, long long a_sk, const float *B,
+                 long long b_sk, long long b_sn, const float *bias, float *C, long long c_sm,
+                 bool accumulate, cudaStream_t st)
+{
+    if (M <= 0 || N <= 0) return C2V_OK;
+    dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
+    sgemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, a_sm, a_sk, B, b_sk, b_sn, bias, C, c_sm,
+                                       accumulate ? 1 : 0);
+    C2V_LAUNCH_OK("sgemm_kernel");
+    return C2V_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// angular-margin head (model.py:71-80): one warp per (bag, class) pair group.
+// ------------------------------------------------------------------------------------
+__global__ void row_inv_norm_kernel(const float *__restrict__ X, long long rows, int H,
+                                    float *__restrict__ inv)
+{
+    const long long r = (long long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.0f;
+    for (int c = lane; c < H; c += 32) { const float v = X[r * H + c]; s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) inv[r] = 1.0f / fmaxf(sqrtf(s), 1e-12f);   // F.normalize eps
+}
+
+__global__ void angular_epilogue_kernel(float *__restrict__ out, const float *__restrict__ inv_cv,
+                                        const float *__restrict__ inv_w,
+                                        const long long *__restrict__ label, int B, long long C,
+                                        float cos_m, float sin_m, float inv_temp)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * C) return;
+    const int b = (int)(i / C);
+    const long long c = i % C;
+    const float cosv = out[i] * inv_cv[b] * inv_w[c];
+    const float sinv = sqrtf(1.0f - cosv * cosv);
+    float phi = cosv * cos_m - sinv * sin_m;
+    if (!(cosv > 0.0f)) phi = cosv;
+    out[i] = (label[b] == c ? phi : cosv) * inv_temp;
+}
+
+int launch_angular(const c2v_dims *d, const c2v_params *p, const float *cv, const long long *label,
+                   int B, float margin, float inverse_temp, float *out, float *scratch,
+                   cudaStream_t st)
+{
+    const int H = d->encode;
+    const long long C = d->label_count;
+    float *inv_cv = scratch, *inv_w = scratch + B;
+    row_inv_norm_kernel<<<(B + 7) / 8, 256, 0, st>>>(cv, B, H, inv_cv);
+    C2V_LAUNCH_OK("row_inv_norm_kernel");
+    row_inv_norm_kernel<<<(unsigned)((C + 7) / 8), 256, 0, st>>>(p->output_weight, C, H, inv_w);
+    C2V_LAUNCH_OK("row_inv_norm_kernel");
+    int rc = launch_sgemm(B, (int)C, H, cv, H, 1, p->output_weight, 1, H, nullptr, out, C, false, st);
+    if (rc != C2V_OK) return rc;
+    const long long n = (long long)B * C;
+    angular_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        out, inv_cv, inv_w, label, B, C, cosf(margin), sinf(margin), inverse_temp);
+    C2V_LAUNCH_OK("angular_epilogue_kernel");
+    return C2V_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// log_softmax + mean NLL + argmax (+ d_outputs) in one pass over the logits per row.
+// One CTA per bag; loss is accumulated with one atomicAdd per bag (pre-zeroed by the host).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+loss_argmax_kernel(const float *__restrict__ out, const long long *__restrict__ label, int B,
+                   long long C, float *__restrict__ loss, long long *__restrict__ argmax,
+                   float *__restrict__ maxval, float *__restrict__ d_out)
+{
+    __shared__ float s_val[8];
+    __shared__ long long s_idx[8];
+    __shared__ float s_sum[8];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *r = out + (size_t)b * C;
+    float mx = -INFINITY; long long am = 0x7fffffffffffffffLL;
+    for (long long c = tid; c < C; c += 256) {
+        const float v = r[c];
+        if (v > mx) { mx = v; am = c; }         // strided scan keeps the first max per thread
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, am, o);
+        if (ov > mx || (ov == mx && oi < am)) { mx = ov; am = oi; }   // torch.max: first max wins
+    }
+    if (lane == 0) { s_val[warp] = mx; s_idx[warp] = am; }
+    __syncthreads();
+    mx = s_val[0]; am = s_idx[0];
+    for (int w = 1; w < 8; ++w)
+        if (s_val[w] > mx || (s_val[w] == mx && s_idx[w] < am)) { mx = s_val[w]; am = s_idx[w]; }
+    float s = 0.0f;
+    for (long long c = tid; c < C; c += 256) s += __expf(r[c] - mx);
+    s = warp_sum(s);
+    if (lane == 0) s_sum[warp] = s;
+    __syncthreads();
+    s = 0.0f;
+    for (int w = 0; w < 8; ++w) s += s_sum[w];
+    if (tid == 0) {
+        if (argmax) argmax[b] = am;
+        if (maxval) maxval[b] = mx;
+        if (loss && label) atomicAdd(loss, (mx + logf(s) - r[label[b]]) / (float)B);
+    }
+    if (d_out && label) {
+        const float inv = 1.0f / s, invB = 1.0f / (float)B;
+        const long long lab = label[b];
+        float *g = d_out + (size_t)b * C;
+        for (long long c = tid; c < C; c += 256)
+            g[c] = (__expf(r[c] - mx) * inv - (c == lab ? 1.0f : 0.0f)) * invB;
+    }
+}
+
+int launch_loss_argmax(const float *out, const long long *label, int B, long long C, float *loss,
+                       long long *argmax, float *maxval, float *d_out, cudaStream_t st)
+{
+    if (loss) C2V_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), st));
+    loss_argmax_kernel<<<B, 256, 0, st>>>(out, label, B, C, loss, argmax, maxval, d_out);
+    C2V_LAUNCH_OK("loss_argmax_kernel");
+    return C2V_OK;
+}
+
+// column sums of d_out [B, C] -> d_bias [C]
+__global__ void colsum_kernel(const float *__restrict__ X, int B, long long C, float *__restrict__ out)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.0f;
+    for (int b = 0; b < B; ++b) s += X[(size_t)b * C + c];
+    out[c] = s;
+}
+int launch_colsum(const float *X, int B, long long C, float *out, cudaStream_t st)
+{
+    colsum_kernel<<<(unsigned)((C + 255) / 256), 256, 0, st>>>(X, B, C, out);
+    C2V_LAUNCH_OK("colsum_kernel");
+    return C2V_OK;
+}
+
+}  // namespace c2v

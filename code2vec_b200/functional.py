@@ -1,0 +1,156 @@
+"""torch-facing wrappers over the C ABI: device memory, streams and autograd plumbing only.
+All arithmetic happens inside libc2v_b200.so."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import Dims, Dropout, Grads, Params
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.C2VError(
+                "code2vec_b200 runs on CUDA (sm_100a) only and has no CPU fallback: got a "
+                f"{t.device} tensor. Move the module and its inputs to a B200 device.")
+
+
+def _idx(t, name, shape=None):
+    if t.dtype != torch.int64:
+        raise TypeError(f"{name} must be int64 (dataset_builder.py:206-209), got {t.dtype}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t.contiguous()
+
+
+def make_dims(T, P, C, Et, Ep, H):
+    return Dims(int(T), int(P), int(C), int(Et), int(Ep), int(H), 0)
+
+
+def make_params(emb_t, emb_p, W, ln_g, ln_b, attn, w_out=None, b_out=None):
+    for t in (emb_t, emb_p, W, ln_g, ln_b, attn, w_out, b_out):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise TypeError("parameters must be contiguous fp32")
+    return Params(_ptr(emb_t), _ptr(emb_p), _ptr(W), _ptr(ln_g), _ptr(ln_b), _ptr(attn), _ptr(w_out), _ptr(b_out))
+
+
+def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False, seed=0, algo=_lib.ALGO_AUTO,
+                   check_indices=False):
+    """-> (code_vector [B,H], attention [B,L]); model.py:48-69 + 90-96."""
+    lib = _lib.load()
+    _need_cuda(starts, paths, ends)
+    B, L = starts.shape
+    starts = _idx(starts, "starts"); paths = _idx(paths, "paths", (B, L)); ends = _idx(ends, "ends", (B, L))
+    dev = starts.device
+    with torch.cuda.device(dev):
+        cv = torch.empty((B, dims.encode), dtype=torch.float32, device=dev)
+        att = torch.empty((B, L), dtype=torch.float32, device=dev)
+        nbytes = lib.c2v_encode_workspace_bytes(ctypes.byref(dims), B, L)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        drop = Dropout(float(drop_p), 1 if training else 0, int(seed))
+        rc = lib.c2v_encode_forward(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
+                                    B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(ws), nbytes, int(algo),
+                                    _stream(dev))
+        _lib.check(rc, "c2v_encode_forward")
+        if check_indices:
+            bad = lib.c2v_workspace_status(_ptr(ws), _stream(dev))
+            if bad > 0:
+                raise IndexError("index out of range in self")
+            if bad < 0:
+                _lib.check(int(bad), "c2v_workspace_status")
+    return cv, att
+
+
+def label_logits(dims, params, cv, algo=_lib.ALGO_AUTO):
+    """model.py:83"""
+    lib = _lib.load()
+    _need_cuda(cv)
+    B = cv.shape[0]
+    dev = cv.device
+    with torch.cuda.device(dev):
+        out = torch.empty((B, dims.label_count), dtype=torch.float32, device=dev)
+        nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        rc = lib.c2v_label_logits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), B, _ptr(out),
+                                  _ptr(ws), nbytes, int(algo), _stream(dev))
+        _lib.check(rc, "c2v_label_logits")
+    return out
+
+
+def angular_logits(dims, params, cv, label, margin, inverse_temp):
+    """model.py:71-80"""
+    lib = _lib.load()
+    _need_cuda(cv, label)
+    B = cv.shape[0]
+    dev = cv.device
+    label = _idx(label, "label", (B,))
+    with torch.cuda.device(dev):
+        out = torch.empty((B, dims.label_count), dtype=torch.float32, device=dev)
+        rc = lib.c2v_angular_logits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), _ptr(label), B,
+                                    float(margin), float(inverse_temp), _ptr(out), _stream(dev))
+        _lib.check(rc, "c2v_angular_logits")
+    return out
+
+
+def loss_argmax(outputs, label=None, want_grad=False):
+    """main.py:251-264 + main.py:285 -> (loss 0-d or None, argmax [B], maxval [B], d_outputs or None)"""
+    lib = _lib.load()
+    _need_cuda(outputs)
+    B, C = outputs.shape
+    dev = outputs.device
+    outputs = outputs.contiguous()
+    with torch.cuda.device(dev):
+        am = torch.empty((B,), dtype=torch.int64, device=dev)
+        mx = torch.empty((B,), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev) if label is not None else None
+        dout = torch.empty_like(outputs) if (want_grad and label is not None) else None
+        if label is not None:
+            label = _idx(label, "label", (B,))
+        rc = lib.c2v_loss_argmax(_ptr(outputs), _ptr(label), B, C, _ptr(loss), _ptr(am), _ptr(mx), _ptr(dout),
+                                 _stream(dev))
+        _lib.check(rc, "c2v_loss_argmax")
+    return loss, am, mx, dout
+
+
+def label_backward(dims, params, cv, d_out, need_cv=True, need_w=True, need_b=True):
+    lib = _lib.load()
+    B = cv.shape[0]
+    dev = cv.device
+    with torch.cuda.device(dev):
+        d_cv = torch.empty_like(cv) if need_cv else None
+        d_w = torch.empty((dims.label_count, dims.encode), dtype=torch.float32, device=dev) if need_w else None
+        d_b = torch.empty((dims.label_count,), dtype=torch.float32, device=dev) if need_b else None
+        rc = lib.c2v_label_backward(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()),
+                                    _ptr(d_out.contiguous()), B, _ptr(d_cv), _ptr(d_w), _ptr(d_b), _stream(dev))
+        _lib.check(rc, "c2v_label_backward")
+    return d_cv, d_w, d_b
+
+
+def encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p=0.0, training=False,
+                    seed=0, grads_out=None):
+    """Gradients of the six encode parameters; returns dict name -> tensor."""
+    lib = _lib.load()
+    B, L = starts.shape
+    dev = starts.device
+    with torch.cuda.device(dev):
+        g = grads_out or {k: torch.zeros(s, dtype=torch.float32, device=dev) for k, s in shapes.items()}
+        grads = Grads(_ptr(g["terminal_embedding"]), _ptr(g["path_embedding"]), _ptr(g["input_linear"]),
+                      _ptr(g["ln_weight"]), _ptr(g["ln_bias"]), _ptr(g["attention"]))
+        nbytes = lib.c2v_encode_backward_workspace_bytes(ctypes.byref(dims), B, L)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        drop = Dropout(float(drop_p), 1 if training else 0, int(seed))
+        rc = lib.c2v_encode_backward(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
+                                     B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(d_cv.contiguous()),
+                                     _ptr(d_att.contiguous()) if d_att is not None else None, ctypes.byref(grads),
+                                     _ptr(ws), nbytes, _stream(dev))
+        _lib.check(rc, "c2v_encode_backward")
+    return g

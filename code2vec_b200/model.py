@@ -1,0 +1,168 @@
+"""Drop-in `Code2Vec` for the reference's `model/model.py`, backed by the sm_100a kernels.
+
+Boundary mirrored:
+  * constructor `Code2Vec(option)` reads the same Option fields (model.py:18-42) and creates
+    the same submodules in the same order, so `torch.manual_seed(s); Code2Vec(option)` gives
+    bit-identical initial weights and `state_dict()` keys/shapes interchange with the reference;
+  * `forward(starts, paths, ends, label) -> (outputs, code_vector, attention)` (model.py:44-88),
+    int64 [b, L] inputs, fp32 outputs, autograd-connected to every parameter;
+  * `model.train()/eval()` toggle dropout only (model.py:60-61);
+  * `from code2vec_b200.model import *` also exports `nn`, `F`, `torch`, `math`, `Parameter`,
+    `NINF`, because the reference's main.py uses `nn` / `F` from that star import
+    (main.py:22, :130, :261).
+
+There is no CPU path: parameters and inputs must live on a CUDA (B200) device.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.parameter import Parameter
+
+from . import _lib
+from . import functional as CF
+
+NINF = - 3.4 * math.pow(10, 38)  # model.py:12
+
+__all__ = ["Code2Vec", "NINF", "torch", "nn", "F", "Parameter", "math"]
+
+
+class _EncodeFn(torch.autograd.Function):
+    """gathers -> concat -> input_linear -> LayerNorm -> tanh -> dropout -> attention -> code vector."""
+
+    @staticmethod
+    def forward(ctx, emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, dims, drop_p, training, seed, algo):
+        params = CF.make_params(emb_t, emb_p, W, ln_g, ln_b, attn)
+        cv, att = CF.encode_forward(dims, params, starts, paths, ends, drop_p, training, seed, algo)
+        ctx.save_for_backward(emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, cv, att)
+        ctx.cfg = (dims, drop_p, training, seed)
+        return cv, att
+
+    @staticmethod
+    def backward(ctx, d_cv, d_att):
+        emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, cv, att = ctx.saved_tensors
+        dims, drop_p, training, seed = ctx.cfg
+        params = CF.make_params(emb_t, emb_p, W, ln_g, ln_b, attn)
+        shapes = {"terminal_embedding": emb_t.shape, "path_embedding": emb_p.shape, "input_linear": W.shape,
+                  "ln_weight": ln_g.shape, "ln_bias": ln_b.shape, "attention": attn.shape}
+        if d_cv is None:
+            d_cv = torch.zeros_like(cv)
+        g = CF.encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p, training, seed)
+        return (g["terminal_embedding"], g["path_embedding"], g["input_linear"], g["ln_weight"], g["ln_bias"],
+                g["attention"], None, None, None, None, None, None, None, None)
+
+
+class _LabelFn(torch.autograd.Function):
+    """outputs = cv . W_out^T + b   (model.py:83)"""
+
+    @staticmethod
+    def forward(ctx, cv, w_out, b_out, dims, algo):
+        params = CF.make_params(None, None, None, None, None, None, w_out, b_out)
+        out = CF.label_logits(dims, params, cv, algo)
+        ctx.save_for_backward(cv, w_out)
+        ctx.dims = dims
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        cv, w_out = ctx.saved_tensors
+        params = CF.make_params(None, None, None, None, None, None, w_out, None)
+        d_cv, d_w, d_b = CF.label_backward(ctx.dims, params, cv, d_out, ctx.needs_input_grad[0],
+                                           ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        return d_cv, d_w, d_b, None, None
+
+
+class Code2Vec(nn.Module):
+    """the code2vec model (B200-native drop-in for model.py:15-105)"""
+
+    def __init__(self, option, algo="auto"):
+        super(Code2Vec, self).__init__()
+        self.option = option
+        # same submodules, same order => same RNG consumption as model.py:21-42
+        self.terminal_embedding = nn.Embedding(option.terminal_count, option.terminal_embed_size)
+        self.path_embedding = nn.Embedding(option.path_count, option.path_embed_size)
+        self.input_linear = nn.Linear(option.terminal_embed_size * 2 + option.path_embed_size, option.encode_size, bias=False)
+        self.input_layer_norm = nn.LayerNorm(option.encode_size)
+
+        if 0.0 < option.dropout_prob < 1.0:
+            self.input_dropout = nn.Dropout(p=option.dropout_prob)   # holds p; the mask is made in-kernel
+        else:
+            self.input_dropout = None
+
+        self.attention_parameter = Parameter(torch.nn.init.xavier_normal_(torch.zeros(option.encode_size, 1, dtype=torch.float32, requires_grad=True)).view(-1), requires_grad=True)
+
+        if option.angular_margin_loss:
+            self.output_linear = Parameter(torch.empty(option.label_count, option.encode_size, dtype=torch.float32))
+            nn.init.xavier_uniform_(self.output_linear)
+            self.cos_m = math.cos(option.angular_margin)
+            self.sin_m = math.sin(option.angular_margin)
+            self.th = math.cos(math.pi - option.angular_margin)
+            self.mm = math.sin(math.pi - option.angular_margin) * option.angular_margin
+        else:
+            self.output_linear = nn.Linear(option.encode_size, option.label_count, bias=True)
+            self.output_linear.bias.data.fill_(0.0)
+
+        self.algo = {"auto": _lib.ALGO_AUTO, "ffma": _lib.ALGO_FFMA, "tcgen05": _lib.ALGO_TCGEN05}[algo]
+        self._dropout_calls = 0
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _dims(self):
+        o = self.option
+        return CF.make_dims(o.terminal_count, o.path_count, o.label_count, o.terminal_embed_size,
+                            o.path_embed_size, o.encode_size)
+
+    def _next_seed(self):
+        # one Philox key per training forward, drawn from torch's CPU generator so that
+        # torch.manual_seed (main.py:120) makes runs repeatable
+        self._dropout_calls += 1
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    # -- the reference surface -------------------------------------------------------------
+    def forward(self, starts, paths, ends, label):
+        option = self.option
+        dims = self._dims()
+        training = self.training and self.input_dropout is not None
+        drop_p = float(option.dropout_prob) if training else 0.0
+        seed = self._next_seed() if training else 0
+
+        code_vector, attention = _EncodeFn.apply(
+            self.terminal_embedding.weight, self.path_embedding.weight, self.input_linear.weight,
+            self.input_layer_norm.weight, self.input_layer_norm.bias, self.attention_parameter,
+            starts, paths, ends, dims, drop_p, training, seed, self.algo)
+
+        if option.angular_margin_loss:
+            if torch.is_grad_enabled() and (code_vector.requires_grad or self.output_linear.requires_grad):
+                # training through the optional angular head: autograd over torch ops
+                # (SURVEY.md 8a row 14 allows a PyTorch epilogue for this mode)
+                cosine = F.linear(F.normalize(code_vector), F.normalize(self.output_linear))
+                sine = torch.sqrt(1.0 - torch.pow(cosine, 2))
+                phi = cosine * self.cos_m - sine * self.sin_m
+                phi = torch.where(cosine > 0, phi, cosine)
+                one_hot = torch.zeros(cosine.size(), device=cosine.device)
+                one_hot.scatter_(1, label.view(-1, 1).long(), 1)
+                outputs = ((one_hot * phi) + ((1.0 - one_hot) * cosine)) * option.inverse_temp
+            else:
+                params = CF.make_params(None, None, None, None, None, None, self.output_linear, None)
+                outputs = CF.angular_logits(dims, params, code_vector, label, option.angular_margin, option.inverse_temp)
+        else:
+            outputs = _LabelFn.apply(code_vector, self.output_linear.weight, self.output_linear.bias, dims,
+                                     _lib.ALGO_FFMA if self.algo == _lib.ALGO_FFMA else _lib.ALGO_AUTO)
+
+        return outputs, code_vector, attention
+
+    # -- additive convenience (the reference does torch.max(preds, dim=1) at main.py:285) ----
+    @torch.no_grad()
+    def predict(self, starts, paths, ends):
+        """-> (pred_label [b], pred_score [b], code_vector [b,H], attention [b,L])"""
+        if self.option.angular_margin_loss:
+            raise NotImplementedError("predict() needs the plain label head (the angular head needs labels)")
+        was = self.training
+        self.eval()
+        try:
+            dummy = torch.zeros((starts.shape[0],), dtype=torch.int64, device=starts.device)
+            outputs, code_vector, attention = self.forward(starts, paths, ends, dummy)
+        finally:
+            self.train(was)
+        _, am, mx, _ = CF.loss_argmax(outputs)
+        return am, mx, code_vector, attention

@@ -1,0 +1,216 @@
+/*
+ * c2v_b200.h -- C ABI of the B200-native code2vec path-attention encoder.
+ *
+ * This is the drop-in boundary for ONE hot path of sonoisa/code2vec:
+ *   Code2Vec.forward(starts, paths, ends, label) -> (outputs, code_vector, attention)
+ *   /root/reference/model/model.py:44-88 (+ get_attention, model.py:90-105),
+ * its autograd backward (what loss.backward() at main.py:174 runs through it) and
+ * the loss/argmax consumers next to it (main.py:251-264, main.py:285).
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); the
+ * binding a maintainer adds is the ctypes stub in INTEGRATION.md, which is what
+ * code2vec_b200/_lib.py contains.  No torch types appear here: plain pointers
+ * and sizes, `void* stream` is a cudaStream_t.
+ *
+ * Conventions
+ *   - all tensors are dense row-major fp32 / int64, exactly the reference's
+ *     dtypes (dataset_builder.py:206-209 builds int64 indices; parameters fp32);
+ *   - "device" entry points take device pointers and never synchronise or
+ *     allocate: the caller passes a workspace of c2v_*_workspace_bytes();
+ *   - "host" entry points take host pointers, copy in/out on the given stream
+ *     and synchronise before returning;
+ *   - every function returns C2V_OK (0) or a negative C2V_E* code;
+ *     c2v_last_error() gives the message for the calling thread.
+ *   - index semantics: starts/ends in [0,T), paths in [0,P).  The reference
+ *     raises IndexError (CPU) / device-asserts (CUDA) on violations
+ *     (SURVEY.md 8b "Call"); here out-of-range indices are clamped to row 0 and
+ *     counted in the workspace status word, which the host entry points turn
+ *     into C2V_EINDEX and c2v_workspace_status() exposes to device callers.
+ */
+#ifndef C2V_B200_H
+#define C2V_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2V_ABI_VERSION 1
+
+enum {
+    C2V_OK = 0,
+    C2V_EINVAL = -1,   /* bad argument (shape, null pointer, alignment)            */
+    C2V_ECUDA = -2,    /* a CUDA runtime call or launch failed                     */
+    C2V_EWORKSPACE = -3, /* workspace too small                                    */
+    C2V_EINDEX = -4,   /* an index was out of range (reference: IndexError)        */
+    C2V_EUNSUPPORTED = -5 /* requested algorithm cannot run this shape / device    */
+};
+
+/* Which encode / GEMM implementation to run. AUTO picks TCGEN05 when the shape
+ * is supported (see c2v_encode_supports_tcgen05) and FFMA otherwise. */
+enum {
+    C2V_ALGO_AUTO = 0,
+    C2V_ALGO_FFMA = 1,    /* fp32 CUDA-core path, any shape                         */
+    C2V_ALGO_TCGEN05 = 2  /* tcgen05.mma kind::f16, 3-pass hi/lo split, fp32-accurate */
+};
+
+/* Sizes read from the reference's Option (main.py:93-115) by Code2Vec.__init__
+ * (model.py:18-42). */
+typedef struct c2v_dims {
+    int64_t terminal_count;   /* T: rows of terminal_embedding   (model.py:21) */
+    int64_t path_count;       /* P: rows of path_embedding       (model.py:22) */
+    int64_t label_count;      /* C: rows of output_linear        (model.py:41) */
+    int32_t terminal_embed;   /* E_t                                            */
+    int32_t path_embed;       /* E_p                                            */
+    int32_t encode;           /* H: input_linear out features    (model.py:23) */
+    int32_t reserved;
+} c2v_dims;
+
+/* Parameters, named as in the reference state_dict. */
+typedef struct c2v_params {
+    const float *terminal_embedding;  /* [T, E_t]              model.py:21 */
+    const float *path_embedding;      /* [P, E_p]              model.py:22 */
+    const float *input_linear;        /* [H, 2E_t+E_p] no bias model.py:23 */
+    const float *ln_weight;           /* [H]                   model.py:24 */
+    const float *ln_bias;             /* [H]                   model.py:24 */
+    const float *attention;           /* [H]                   model.py:31 */
+    const float *output_weight;       /* [C, H]                model.py:33/41 */
+    const float *output_bias;         /* [C] or NULL (angular) model.py:41-42 */
+} c2v_params;
+
+/* Gradients, same shapes as c2v_params.  The embedding / linear gradients are
+ * ACCUMULATED into (atomics), so the caller zero-fills them (optimizer.zero_grad,
+ * main.py:171); the small ones are overwritten. */
+typedef struct c2v_grads {
+    float *terminal_embedding;
+    float *path_embedding;
+    float *input_linear;
+    float *ln_weight;
+    float *ln_bias;
+    float *attention;
+} c2v_grads;
+
+/* Dropout after tanh (model.py:26-29, :60-61): keep-prob 1-p, survivors scaled by
+ * 1/(1-p).  The mask is a counter-based hash of (seed, context row, column), so
+ * backward regenerates it instead of storing it. training==0 or p outside (0,1)
+ * means identity, as in the reference. */
+typedef struct c2v_dropout {
+    float p;
+    int32_t training;
+    uint64_t seed;
+} c2v_dropout;
+
+int c2v_abi_version(void);
+const char *c2v_last_error(void);
+
+/* Device facts the host side sizes grids with. */
+typedef struct c2v_device_info {
+    int32_t cc_major, cc_minor, sm_count, reserved;
+    int64_t global_mem_bytes;
+    int64_t smem_per_block_optin;
+} c2v_device_info;
+int c2v_get_device_info(int device, c2v_device_info *out);
+
+/* 1 if the tcgen05 encode kernel handles this shape on this device. */
+int c2v_encode_supports_tcgen05(const c2v_dims *d);
+
+/* ---- encode: model.py:48-69 + 90-96 as one fused pass ------------------------------
+ * gathers -> concat -> input_linear -> LayerNorm -> tanh -> dropout -> masked
+ * attention softmax over the bag -> weighted sum.
+ *   starts/paths/ends : int64 [B, L] device
+ *   code_vector [B, H], attention [B, L] : fp32 device, overwritten
+ * Workspace holds the split weights, the per-(tile,bag) softmax partials and a
+ * status word; contents are needed by c2v_encode_backward for the same batch. */
+size_t c2v_encode_workspace_bytes(const c2v_dims *d, int32_t B, int32_t L);
+int c2v_encode_forward(const c2v_dims *d, const c2v_params *p,
+                       const int64_t *starts, const int64_t *paths, const int64_t *ends,
+                       int32_t B, int32_t L, const c2v_dropout *drop,
+                       float *code_vector, float *attention,
+                       void *workspace, size_t workspace_bytes, int32_t algo, void *stream);
+
+/* Reads the status word of the last encode on this workspace (synchronises the
+ * stream): returns the number of out-of-range indices seen, or a negative code. */
+int64_t c2v_workspace_status(void *workspace, void *stream);
+
+/* ---- label head --------------------------------------------------------------------
+ * plain:   outputs = cv . W_out^T + b                                   model.py:83
+ * angular: cosine head with margin on the true class, times inverse_temp model.py:71-80
+ *          (needs label, also in eval).
+ * cv [B,H], outputs [B,C] device fp32; label int64 [B] device. */
+size_t c2v_label_workspace_bytes(const c2v_dims *d, int32_t B);
+int c2v_label_logits(const c2v_dims *d, const c2v_params *p, const float *code_vector, int32_t B,
+                     float *outputs, void *workspace, size_t workspace_bytes, int32_t algo,
+                     void *stream);
+int c2v_angular_logits(const c2v_dims *d, const c2v_params *p, const float *code_vector,
+                       const int64_t *label, int32_t B, float margin, float inverse_temp,
+                       float *outputs, void *stream);
+
+/* ---- loss / predict next to the path ----------------------------------------------
+ * main.py:251-264: mean over the batch of -log_softmax(outputs)[label] (NLLLoss
+ * weights are identically 1); main.py:285: torch.max(dim=1).
+ * Any of loss / argmax / maxval / d_outputs may be NULL.  d_outputs [B,C] receives
+ * dLoss/doutputs = (softmax - onehot) / B. */
+int c2v_loss_argmax(const float *outputs, const int64_t *label, int32_t B, int64_t C,
+                    float *loss, int64_t *argmax, float *maxval, float *d_outputs, void *stream);
+
+/* ---- backward ----------------------------------------------------------------------
+ * Label head: d_cv = d_out . W_out ; dW_out = d_out^T . cv ; d_bias = sum_b d_out. */
+int c2v_label_backward(const c2v_dims *d, const c2v_params *p, const float *code_vector,
+                       const float *d_outputs, int32_t B, float *d_code_vector,
+                       float *d_output_weight, float *d_output_bias, void *stream);
+/* Encode: gradients of every encode parameter given d_code_vector [B,H] and
+ * (optionally, may be NULL) d_attention [B,L]; formulas in DESIGN.md "Backward".
+ * Recomputes the forward per context row (nothing but code_vector / attention is
+ * stashed) and regenerates the dropout mask from `drop`. */
+size_t c2v_encode_backward_workspace_bytes(const c2v_dims *d, int32_t B, int32_t L);
+int c2v_encode_backward(const c2v_dims *d, const c2v_params *p,
+                        const int64_t *starts, const int64_t *paths, const int64_t *ends,
+                        int32_t B, int32_t L, const c2v_dropout *drop,
+                        const float *code_vector, const float *attention,
+                        const float *d_code_vector, const float *d_attention,
+                        const c2v_grads *grads, void *workspace, size_t workspace_bytes,
+                        void *stream);
+
+/* ---- host-buffer call: what a reference-side caller with CPU tensors uses ----------
+ * One whole Code2Vec.forward + torch.max for a batch held in HOST memory (pinned
+ * for full speed): copies the int64 indices in, runs encode + label head +
+ * argmax on `device`, copies code_vector / attention / prediction (and the
+ * logits, if `outputs` is not NULL) back, synchronises.  Parameters stay on the
+ * device (p holds device pointers).  Returns C2V_EINDEX if an index was out of
+ * range.  `session` keeps the device staging buffers between calls. */
+typedef struct c2v_session c2v_session;
+int c2v_session_create(int device, const c2v_dims *d, int32_t max_B, int32_t L, c2v_session **out);
+void c2v_session_destroy(c2v_session *s);
+int c2v_forward_host(c2v_session *s, const c2v_params *p,
+                     const int64_t *starts, const int64_t *paths, const int64_t *ends,
+                     const int64_t *label, int32_t B,
+                     float *outputs /* [B,C] or NULL */, float *code_vector /* [B,H] */,
+                     float *attention /* [B,L] */, int64_t *pred_label /* [B] or NULL */,
+                     float *pred_score /* [B] or NULL */, int32_t algo);
+/* Pipelined variant: enqueue only (H2D, kernels, D2H on the session's streams);
+ * c2v_session_wait() blocks until batch `ticket` has fully landed in the host
+ * buffers.  Lets step i+1's H2D overlap step i's kernels (double buffered). */
+int c2v_forward_host_async(c2v_session *s, const c2v_params *p,
+                           const int64_t *starts, const int64_t *paths, const int64_t *ends,
+                           const int64_t *label, int32_t B,
+                           float *outputs, float *code_vector, float *attention,
+                           int64_t *pred_label, float *pred_score, int32_t algo, int64_t *ticket);
+int c2v_session_wait(c2v_session *s, int64_t ticket);
+
+/* Counts kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t c2v_launch_count(void);
+
+/* Measurement hook for bench.py's roofline: while enabled, every c2v_encode_forward brackets
+ * its dominant kernel (the fused gather+encode+attention kernel, not the weight prep or the
+ * per-bag finalize) with CUDA events on the launching stream.  c2v_profile_read synchronises
+ * those events and returns the summed kernel milliseconds and the launch count since the last
+ * enable; timing never runs under a profiler and adds no device work. */
+int c2v_profile_enable(int32_t on);
+int c2v_profile_read(double *kernel_ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2V_B200_H */

@@ -1,0 +1,203 @@
+"""-m gpu parity tests of the CUDA path (through the C ABI) against
+ (1) the committed outputs of the unmodified reference (tests/golden/), bar: 1e-4 fp32 abs
+     (BASELINE.json north_star), observed ~1e-6;
+ (2) the CPU oracle on fresh seeded inputs at sizes it finishes in seconds;
+ (3) size-independent properties at BASELINE.json's full batch (1024 x 200)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from gpu_util import ALGOS, algos_for, cuda, model_from_golden, random_batch, random_params, supports_tcgen05
+from code2vec_b200 import _lib
+from code2vec_b200 import functional as CF
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4          # the north_star's bar
+EXPECT = 2e-5       # what the kernels actually deliver (tighter regression guard)
+
+FWD_CASES = [(n, a) for n in golden_names() for a in ("ffma", "tcgen05")]
+
+
+@pytest.mark.parametrize("name,algo", FWD_CASES)
+def test_forward_matches_reference_golden(name, algo):
+    rec = load_golden(name)
+    if algo == "tcgen05" and not supports_tcgen05(rec["opt"]):
+        pytest.skip("shape not handled by the tcgen05 kernel (FFMA path covers it)")
+    m = model_from_golden(rec, algo=algo).eval()
+    with torch.no_grad():
+        out, cv, att = m.forward(cuda(rec["starts"]), cuda(rec["paths"]), cuda(rec["ends"]), cuda(rec["label"]))
+    torch.cuda.synchronize()
+    scale = max(1.0, float(np.abs(rec["outputs"]).max()))
+    e_cv = np.abs(cv.cpu().numpy() - rec["code_vector"]).max()
+    e_att = np.abs(att.cpu().numpy() - rec["attention"]).max()
+    e_out = np.abs(out.cpu().numpy() - rec["outputs"]).max()
+    assert e_cv <= EXPECT and e_att <= EXPECT and e_out <= EXPECT * scale * 4, (e_cv, e_att, e_out)
+    assert e_cv <= TOL and e_att <= TOL
+    # padded slots are exactly zero whenever the bag has a valid context
+    a = att.cpu().numpy()
+    valid = rec["starts"] > 0
+    has_valid = valid.any(1)
+    assert (a[has_valid][~valid[has_valid]] == 0.0).all()
+    assert np.allclose(a.sum(1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("algo", ["ffma", "tcgen05"])
+@pytest.mark.parametrize("B,L", [(1, 1), (3, 200), (64, 200), (37, 50), (130, 31), (7, 333)])
+def test_forward_matches_oracle_on_seeded_inputs(algo, B, L):
+    from oracle import oracle
+    rng = np.random.default_rng(1000 + B * 7 + L)
+    T, P, C, E, H = 5000, 3000, 77, 128, 128
+    p = random_params(rng, T, P, C, E, E, H)
+    starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
+    if B > 2:
+        starts[1, :] = 0                      # an all-pad bag
+        starts[2, ::3] = 0                    # holes
+    dims = CF.make_dims(T, P, C, E, E, H)
+    tp = {k: cuda(v) for k, v in p.items()}
+    params = CF.make_params(tp["terminal_embedding.weight"], tp["path_embedding.weight"], tp["input_linear.weight"],
+                            tp["input_layer_norm.weight"], tp["input_layer_norm.bias"], tp["attention_parameter"],
+                            tp["output_linear.weight"], tp["output_linear.bias"])
+    cv, att = CF.encode_forward(dims, params, cuda(starts), cuda(paths), cuda(ends), algo=ALGOS[algo], check_indices=True)
+    out = CF.label_logits(dims, params, cv, algo=_lib.ALGO_FFMA)
+    ref_out, ref_cv, ref_att = oracle.forward(p, starts, paths, ends, label)
+    assert np.abs(cv.cpu().numpy() - ref_cv).max() <= EXPECT
+    assert np.abs(att.cpu().numpy() - ref_att).max() <= EXPECT
+    assert np.abs(out.cpu().numpy() - ref_out).max() <= EXPECT * 4
+
+
+@pytest.mark.parametrize("algo", ["ffma", "tcgen05"])
+def test_full_size_properties(algo):
+    """BASELINE.json cfg2 batch (1024 x 200, E=H=128): too big for the scalar oracle, so check
+    properties: rows of attention sum to 1, code vectors are convex combinations of tanh outputs
+    (|cv| <= 1), the two algorithms agree, bags are independent of their batch neighbours, and a
+    random sample of bags matches the oracle."""
+    from oracle import oracle
+    rng = np.random.default_rng(7)
+    T, P, C, E, H, B, L = 50000, 40000, 512, 128, 128, 1024, 200
+    p = random_params(rng, T, P, C, E, E, H)
+    starts, paths, ends, label = random_batch(rng, B, L, T, P, C, ragged=False)
+    dims = CF.make_dims(T, P, C, E, E, H)
+    tp = {k: cuda(v) for k, v in p.items()}
+    params = CF.make_params(tp["terminal_embedding.weight"], tp["path_embedding.weight"], tp["input_linear.weight"],
+                            tp["input_layer_norm.weight"], tp["input_layer_norm.bias"], tp["attention_parameter"],
+                            tp["output_linear.weight"], tp["output_linear.bias"])
+    s, pp, e = cuda(starts), cuda(paths), cuda(ends)
+    cv, att = CF.encode_forward(dims, params, s, pp, e, algo=ALGOS[algo], check_indices=True)
+    a = att.cpu().numpy(); v = cv.cpu().numpy()
+    assert np.allclose(a.sum(1), 1.0, atol=2e-5) and (a >= 0).all()
+    assert np.abs(v).max() <= 1.0 + 1e-6
+    sel = rng.choice(B, 12, replace=False)
+    ref_cv, ref_att = oracle.encode_forward(starts[sel], paths[sel], ends[sel], p["terminal_embedding.weight"],
+                                            p["path_embedding.weight"], p["input_linear.weight"],
+                                            p["input_layer_norm.weight"], p["input_layer_norm.bias"],
+                                            p["attention_parameter"])
+    assert np.abs(v[sel] - ref_cv).max() <= EXPECT and np.abs(a[sel] - ref_att).max() <= EXPECT
+    # independence: the same bags in a different batch position / batch size give the same rows
+    perm = rng.permutation(B)[:300]
+    cv2, att2 = CF.encode_forward(dims, params, s[perm].contiguous(), pp[perm].contiguous(), e[perm].contiguous(),
+                                  algo=ALGOS[algo])
+    assert np.abs(cv2.cpu().numpy() - v[perm]).max() <= 2e-6
+    other = "ffma" if algo == "tcgen05" else "tcgen05"
+    cv3, att3 = CF.encode_forward(dims, params, s, pp, e, algo=ALGOS[other])
+    assert np.abs(cv3.cpu().numpy() - v).max() <= EXPECT and np.abs(att3.cpu().numpy() - a).max() <= EXPECT
+
+
+def test_out_of_range_index_is_reported_like_the_reference():
+    rec = load_golden("cfg2_small")
+    m = model_from_golden(rec).eval()
+    bad = rec["starts"].copy(); bad[0, 0] = rec["opt"]["T"]
+    o = rec["opt"]
+    dims = CF.make_dims(o["T"], o["P"], o["C"], o["Et"], o["Ep"], o["H"])
+    params = CF.make_params(m.terminal_embedding.weight.data, m.path_embedding.weight.data, m.input_linear.weight.data,
+                            m.input_layer_norm.weight.data, m.input_layer_norm.bias.data, m.attention_parameter.data)
+    for algo in algos_for(o):
+        with pytest.raises(IndexError):
+            CF.encode_forward(dims, params, cuda(bad), cuda(rec["paths"]), cuda(rec["ends"]), algo=ALGOS[algo],
+                              check_indices=True)
+
+
+@pytest.mark.parametrize("algo", ["ffma", "tcgen05"])
+def test_training_mode_dropout_matches_oracle_with_same_mask(algo):
+    """model.py:60-61.  The kernel's mask is a pure function of (seed, row, col); the test rebuilds
+    it in numpy (tests/philox_ref.py) and hands it to the oracle, so parity is exact."""
+    from oracle import oracle
+    from philox_ref import dropout_mask
+    rng = np.random.default_rng(3)
+    T, P, C, E, H, B, L = 900, 700, 33, 128, 128, 9, 200
+    p = random_params(rng, T, P, C, E, E, H)
+    starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
+    dims = CF.make_dims(T, P, C, E, E, H)
+    tp = {k: cuda(v) for k, v in p.items()}
+    params = CF.make_params(tp["terminal_embedding.weight"], tp["path_embedding.weight"], tp["input_linear.weight"],
+                            tp["input_layer_norm.weight"], tp["input_layer_norm.bias"], tp["attention_parameter"])
+    seed, prob = 0x1234567890ABCDEF, 0.25
+    cv, att = CF.encode_forward(dims, params, cuda(starts), cuda(paths), cuda(ends), drop_p=prob, training=True,
+                                seed=seed, algo=ALGOS[algo])
+    mask = dropout_mask(seed, B * L, H, prob).reshape(B, L, H)
+    assert abs((mask > 0).mean() - 0.75) < 0.01
+    ref_cv, ref_att = oracle.encode_forward(starts, paths, ends, p["terminal_embedding.weight"],
+                                            p["path_embedding.weight"], p["input_linear.weight"],
+                                            p["input_layer_norm.weight"], p["input_layer_norm.bias"],
+                                            p["attention_parameter"], dropmask=mask)
+    assert np.abs(cv.cpu().numpy() - ref_cv).max() <= EXPECT
+    assert np.abs(att.cpu().numpy() - ref_att).max() <= EXPECT
+    # eval mode ignores p
+    cv_e, _ = CF.encode_forward(dims, params, cuda(starts), cuda(paths), cuda(ends), drop_p=prob, training=False,
+                                seed=seed, algo=ALGOS[algo])
+    cv_0, _ = CF.encode_forward(dims, params, cuda(starts), cuda(paths), cuda(ends), algo=ALGOS[algo])
+    assert torch.equal(cv_e, cv_0)
+
+
+def test_loss_and_argmax_match_oracle():
+    from oracle import oracle
+    rec = load_golden("trained_scale")
+    out = cuda(rec["outputs"]); label = cuda(rec["label"])
+    loss, am, mx, dout = CF.loss_argmax(out, label, want_grad=True)
+    ref_loss, ref_am, ref_mx = oracle.loss_argmax(rec["outputs"], rec["label"])
+    assert abs(loss.item() - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+    assert np.array_equal(am.cpu().numpy(), ref_am) and np.array_equal(mx.cpu().numpy(), ref_mx)
+    t = torch.from_numpy(rec["outputs"]).double().requires_grad_(True)
+    torch.nn.functional.nll_loss(torch.log_softmax(t, 1), torch.from_numpy(rec["label"])).backward()
+    assert np.abs(dout.cpu().numpy() - t.grad.numpy()).max() <= 1e-6
+
+
+def test_host_buffer_api_matches_device_api():
+    """c2v_forward_host: the call a reference-side user with CPU tensors makes."""
+    import ctypes
+    rec = load_golden("cfg2_small")
+    m = model_from_golden(rec).eval()
+    o = rec["opt"]
+    B, L = rec["starts"].shape
+    dims = CF.make_dims(o["T"], o["P"], o["C"], o["Et"], o["Ep"], o["H"])
+    params = CF.make_params(m.terminal_embedding.weight.data, m.path_embedding.weight.data, m.input_linear.weight.data,
+                            m.input_layer_norm.weight.data, m.input_layer_norm.bias.data, m.attention_parameter.data,
+                            m.output_linear.weight.data, m.output_linear.bias.data)
+    lib = _lib.load()
+    sess = ctypes.c_void_p()
+    _lib.check(lib.c2v_session_create(0, ctypes.byref(dims), 16, L, ctypes.byref(sess)), "session_create")
+    try:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        hs, hp, he, hl = pin(rec["starts"]), pin(rec["paths"]), pin(rec["ends"]), pin(rec["label"])
+        out = torch.empty((B, o["C"]), dtype=torch.float32).pin_memory()
+        cv = torch.empty((B, o["H"]), dtype=torch.float32).pin_memory()
+        att = torch.empty((B, L), dtype=torch.float32).pin_memory()
+        pred = torch.empty((B,), dtype=torch.int64).pin_memory()
+        score = torch.empty((B,), dtype=torch.float32).pin_memory()
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        for _ in range(3):   # exercises both staging slots
+            rc = lib.c2v_forward_host(sess, ctypes.byref(params), P(hs), P(hp), P(he), P(hl), B, P(out), P(cv), P(att),
+                                      P(pred), P(score), _lib.ALGO_AUTO)
+            _lib.check(rc, "c2v_forward_host")
+        assert np.abs(cv.numpy() - rec["code_vector"]).max() <= EXPECT
+        assert np.abs(att.numpy() - rec["attention"]).max() <= EXPECT
+        assert np.abs(out.numpy() - rec["outputs"]).max() <= EXPECT * 4
+        assert np.array_equal(pred.numpy(), rec["outputs"].argmax(1))
+        bad = rec["starts"].copy(); bad[1, 2] = -5
+        hb = pin(bad)
+        rc = lib.c2v_forward_host(sess, ctypes.byref(params), P(hb), P(hp), P(he), P(hl), B, None, P(cv), P(att),
+                                  None, None, _lib.ALGO_AUTO)
+        assert rc == _lib.C2V_EINDEX
+    finally:
+        lib.c2v_session_destroy(sess)
