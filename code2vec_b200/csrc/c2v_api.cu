@@ -32,6 +32,8 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
                            const float *d_att, const c2v_grads *g, void *ws, size_t ws_bytes,
                            cudaStream_t st);
 size_t encode_backward_workspace_bytes(const c2v_dims *d, int B, int L);
+bool label_tcgen05_shape_ok(const c2v_dims *d);
+size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B);
 
 // ---- profiling hook (c2v_profile_enable / c2v_profile_read) ----------------------------
 static const int kProfRing = 256;
@@ -247,12 +249,8 @@ int64_t c2v_workspace_status(void *workspace, void *stream)
 size_t c2v_label_workspace_bytes(const c2v_dims *d, int32_t B)
 {
     if (!dims_ok(d) || B < 1) return 0;
-    const size_t hp = (size_t)(d->encode + 63) / 64 * 64;
-    const size_t cp = (size_t)(d->label_count + 127) / 128 * 128;
-    const size_t bp = (size_t)(B + 127) / 128 * 128;
-    // split fp16 copies of cv and W_out for the tcgen05 label GEMM + angular scratch
-    return align_up(2 * cp * hp * 2, 1024) + align_up(2 * bp * hp * 2, 1024) +
-           align_up((size_t)(B + d->label_count) * 4, 1024) + 1024;
+    // split fp16 images of cv and W_out for the tcgen05 label GEMM (unused by the FFMA path)
+    return align_up(label_tcgen05_workspace_bytes(d, B), 1024);
 }
 
 int c2v_label_logits(const c2v_dims *d, const c2v_params *p, const float *code_vector, int32_t B,
@@ -267,7 +265,7 @@ int c2v_label_logits(const c2v_dims *d, const c2v_params *p, const float *code_v
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int H = d->encode;
     const long long C = d->label_count;
-    if (algo == C2V_ALGO_TCGEN05) {
+    if (algo == C2V_ALGO_TCGEN05 || (algo == C2V_ALGO_AUTO && label_tcgen05_shape_ok(d))) {
         return launch_label_tcgen05(d, code_vector, B, p->output_weight, p->output_bias, outputs,
                                     workspace, workspace_bytes, st);
     }

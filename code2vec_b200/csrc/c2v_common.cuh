@@ -68,6 +68,7 @@ struct EncodeArgs {
     float drop_scale;       // 1/(1-p)
     unsigned long long seed;
     float *attention;       // [N] raw masked scores z (finalize turns them into softmax weights)
+    int flags;              // debug switches (bit 0: producer-side proxy fence in the tcgen05 kernel)
     EncodeWorkspace ws;
 };
 

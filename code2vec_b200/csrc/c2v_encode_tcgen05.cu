@@ -11,18 +11,21 @@
 // fp16 subnormals; the epilogue folds the exact inverse into the LayerNorm scale.
 // Measured distance to the reference: ~5e-7 (tests/test_forward_parity_gpu.py).
 //
-// Structure (one persistent CTA per SM, 16 warps, warp-specialised):
-//   warps 0-3   epilogue: TMEM -> registers (one context row per thread), LayerNorm, tanh,
+// Structure (one persistent CTA per SM, 28 warps, warp-specialised):
+//   warps 0-7   epilogue: TMEM -> registers.  Warps q and q+4 share the 32 context rows of TMEM
+//               lane quarter q and take 64 columns each (LayerNorm moments and the score are
+//               exchanged through 3 KB of smem + a 64-thread named barrier); LayerNorm, tanh,
 //               dropout, score, per-warp online-softmax partials (butterfly transpose-reduce)
-//   warps 4-11  A producers: 128-bit coalesced gathers of the fp32 embedding rows, hi/lo fp16
+//   warps 8-23  A producers: 128-bit coalesced gathers of the fp32 embedding rows, hi/lo fp16
 //               split in registers, st.shared into the UMMA K-major SWIZZLE_128B layout
-//   warp 12     MMA issuer (one elected thread): 12 tcgen05.mma per 64-wide k-block
-//   warp 13     W producer: one 32 KB cp.async.bulk (TMA bulk copy) per k-block of the
+//   warp 24     MMA issuer (one elected thread): 12 tcgen05.mma per 64-wide k-block
+//   warp 25     W producer: one 32 KB cp.async.bulk (TMA bulk copy) per k-block of the
 //               pre-split, pre-swizzled weight image
-//   warp 14     TMEM allocator
+//   warp 26     TMEM allocator
 // A 3-stage mbarrier ring carries {A_hi, A_lo, W_hi, W_lo} k-blocks (64 KB per stage);
 // two 128-column TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "c2v_common.cuh"
 
@@ -39,14 +42,21 @@ constexpr int STAGES = 3;
 constexpr int TILE_BYTES = ROWS * KB * 2; // 16 KB: one [128 x 64] fp16 K-major SW128 tile
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // A_hi | A_lo | W_hi | W_lo
 constexpr int W_KB_BYTES = 2 * TILE_BYTES;    // W_hi | W_lo of one k-block, contiguous in HBM
-constexpr int THREADS = 512;
-constexpr int N_PRODUCER_WARPS = 8;
+constexpr int N_EPI_WARPS = 8;
+constexpr int N_PRODUCER_WARPS = 16;
+constexpr int PROD_WARP0 = N_EPI_WARPS;                    // 8
+constexpr int MISC_WARP0 = PROD_WARP0 + N_PRODUCER_WARPS;  // 24
+constexpr int THREADS = (MISC_WARP0 + 4) * 32;             // 896
+constexpr int ROWS_PER_PW = ROWS / N_PRODUCER_WARPS;       // 8 rows of every tile per producer warp
+constexpr int LDG_PER_ITEM = ROWS_PER_PW / 2;              // 4 x LDG.128 (two half rows each)
 constexpr int TMEM_COLS = 256;            // 2 accumulators x 128 fp32 columns
 constexpr int VROWS = 32;                 // rows per partial ("virtual tile" = one epilogue warp)
 // dynamic smem: [<=1023 B align pad][STAGES x 64 KB][gamma|beta|attn 1.5 KB][barriers]
 constexpr int SMEM_VEC_OFF = STAGES * STAGE_BYTES;
-constexpr int SMEM_BAR_OFF = SMEM_VEC_OFF + 3 * H * 4;
+constexpr int SMEM_XCH_OFF = SMEM_VEC_OFF + 3 * H * 4;       // [4 quarters][2 halves][3][32] floats
+constexpr int SMEM_BAR_OFF = SMEM_XCH_OFF + 4 * 2 * 3 * 32 * 4;
 constexpr int SMEM_BYTES = SMEM_BAR_OFF + 128 + 1024;
+constexpr float TWO_LOG2E = 2.8853900817779268f;
 // instruction descriptor, kind::f16: D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 @17, M>>4 @24
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 }  // namespace tc
@@ -214,6 +224,25 @@ int launch_split_w_tcgen05(const c2v_dims *d, const float *W, EncodeWorkspace &w
 // ------------------------------------------------------------------------------------
 struct ProducerIdx { long long s, p, e; };
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// tanh(v) given w = 2*log2(e)*v :  1 - 2/(2^w + 1); 2^w = inf -> 1, 2^w = 0 -> -1.  Two MUFU ops,
+// absolute error ~2e-7 (same formula as tanh_accurate, constants folded into gamma/beta).
+__device__ __forceinline__ float tanh_from_scaled(float w) {
+    return fmaf(-2.0f, rcp_approx(ex2_approx(w) + 1.0f), 1.0f);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __global__ void __launch_bounds__(tc::THREADS, 1)
 encode_tcgen05_kernel(const EncodeArgs a)
 {
@@ -221,7 +250,8 @@ encode_tcgen05_kernel(const EncodeArgs a)
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B tiles need 1024-B alignment
     unsigned char *smem = smem_raw + (base - raw);
-    float *s_vec = reinterpret_cast<float *>(smem + tc::SMEM_VEC_OFF);     // gamma | beta | attn
+    float *s_vec = reinterpret_cast<float *>(smem + tc::SMEM_VEC_OFF);     // gamma' | beta' | attn
+    float *s_xch = reinterpret_cast<float *>(smem + tc::SMEM_XCH_OFF);
     const uint32_t bar_base = base + tc::SMEM_BAR_OFF;
     // barriers (8 B each): full[3] @0, empty[3] @24, tmem_full[2] @48, tmem_empty[2] @64, tmem ptr @80
     const uint32_t bar_full = bar_base, bar_empty = bar_base + 24, bar_tfull = bar_base + 48,
@@ -237,74 +267,87 @@ encode_tcgen05_kernel(const EncodeArgs a)
             mbar_init(bar_full + 8 * s, tc::N_PRODUCER_WARPS + 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, tc::N_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 14) {
+    if (warp == tc::MISC_WARP0 + 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)tc::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid < 3 * tc::H) {
+        // LayerNorm affine pre-multiplied by 2*log2(e) so tanh needs no extra multiply
         const int which = tid / tc::H, c = tid % tc::H;
-        s_vec[tid] = which == 0 ? a.ln_g[c] : which == 1 ? a.ln_b[c] : a.attn[c];
+        s_vec[tid] = which == 0 ? a.ln_g[c] * tc::TWO_LOG2E : which == 1 ? a.ln_b[c] * tc::TWO_LOG2E : a.attn[c];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp < 4) {
+    if (warp < tc::N_EPI_WARPS) {
         // =============================== EPILOGUE ===============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+        const int q = warp & 3;                 // TMEM lane quarter: rows 32q .. 32q+31 of the tile
+        const int hf = warp >> 2;               // column half: 64*hf .. 64*hf+63
+        constexpr int HC = tc::H / 2;           // 64 columns per thread
         const float inv_scale = a.ws.prep_hdr[0];
-        const float4 *sG = reinterpret_cast<const float4 *>(s_vec);
-        const float4 *sB = reinterpret_cast<const float4 *>(s_vec + tc::H);
-        const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * tc::H);
+        const float4 *sG = reinterpret_cast<const float4 *>(s_vec + hf * HC);
+        const float4 *sB = reinterpret_cast<const float4 *>(s_vec + tc::H + hf * HC);
+        const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * tc::H + hf * HC);
+        float *my_x = s_xch + ((q * 2 + hf) * 3) * 32 + lane;          // [3][32] per (quarter, half)
+        const float *ot_x = s_xch + ((q * 2 + (hf ^ 1)) * 3) * 32 + lane;
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
             const int acc = tl & 1;
             const uint32_t acc_phase = (uint32_t)(tl >> 1) & 1u;
-            const long long vrow0 = (long long)tile * tc::ROWS + warp * tc::VROWS;
+            const long long vrow0 = (long long)tile * tc::ROWS + q * tc::VROWS;
             const long long row = vrow0 + lane;
             const bool in_range = row < a.N;
             const long long st_idx = in_range ? a.starts[row] : 0;       // model.py:64 mask = starts > 0
 
             mbar_wait(bar_tfull + 8 * acc, acc_phase, status);
             tc_fence_after();
-            float x[tc::H];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * tc::H);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(taddr + c * 32, x + c * 32);
+            float x[HC];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * tc::H + hf * HC);
+            tmem_ld32(taddr, x);
+            tmem_ld32(taddr + 32, x + 32);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);           // accumulator is free again
 
-            // LayerNorm (model.py:55-56), two-pass in registers; x is scale * (c . W^T)
+            // LayerNorm (model.py:55-56), two-pass; x is scale * (c . W^T); halves exchanged via smem
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int c = 0; c < tc::H; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
-            const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / tc::H);
+            for (int c = 0; c < HC; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
+            float part = (s0 + s1) + (s2 + s3);
+            my_x[0] = part;
+            named_bar_sync(1 + q, 64);
+            const float mean = (part + ot_x[0]) * (1.0f / tc::H);
             s0 = s1 = s2 = s3 = 0.f;
 #pragma unroll
-            for (int c = 0; c < tc::H; c += 4) {
+            for (int c = 0; c < HC; c += 4) {
                 const float d0 = x[c] - mean, d1 = x[c + 1] - mean, d2 = x[c + 2] - mean, d3 = x[c + 3] - mean;
                 s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
             }
-            const float var = ((s0 + s1) + (s2 + s3)) * (1.0f / tc::H) * inv_scale * inv_scale;
+            part = (s0 + s1) + (s2 + s3);
+            my_x[32] = part;
+            named_bar_sync(1 + q, 64);
+            const float var = (part + ot_x[32]) * (1.0f / tc::H) * inv_scale * inv_scale;
             const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
+            const float shift = -mean * nrm;
             // tanh (model.py:57), dropout (model.py:60-61), score h.a (model.py:92-93)
             float u0 = 0.f, u1 = 0.f;
 #pragma unroll
-            for (int c4 = 0; c4 < tc::H / 4; ++c4) {
+            for (int c4 = 0; c4 < HC / 4; ++c4) {
                 const float4 g = sG[c4], b = sB[c4], at = sA[c4];
-                float y0 = tanh_accurate(fmaf((x[4 * c4 + 0] - mean) * nrm, g.x, b.x));
-                float y1 = tanh_accurate(fmaf((x[4 * c4 + 1] - mean) * nrm, g.y, b.y));
-                float y2 = tanh_accurate(fmaf((x[4 * c4 + 2] - mean) * nrm, g.z, b.z));
-                float y3 = tanh_accurate(fmaf((x[4 * c4 + 3] - mean) * nrm, g.w, b.w));
+                float y0 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 0], nrm, shift), g.x, b.x));
+                float y1 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 1], nrm, shift), g.y, b.y));
+                float y2 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 2], nrm, shift), g.z, b.z));
+                float y3 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 3], nrm, shift), g.w, b.w));
                 if (a.drop_p > 0.0f) {
-                    const uint4 bits = dropout_bits(a.seed, row, c4);
+                    const uint4 bits = dropout_bits(a.seed, row, hf * (HC / 4) + c4);
                     y0 *= dropout_mul(bits.x, a.drop_p, a.drop_scale);
                     y1 *= dropout_mul(bits.y, a.drop_p, a.drop_scale);
                     y2 *= dropout_mul(bits.z, a.drop_p, a.drop_scale);
@@ -314,11 +357,16 @@ encode_tcgen05_kernel(const EncodeArgs a)
                 u0 = fmaf(y0, at.x, u0); u1 = fmaf(y1, at.y, u1);
                 u0 = fmaf(y2, at.z, u0); u1 = fmaf(y3, at.w, u1);
             }
+            part = u0 + u1;
+            my_x[64] = part;
+            named_bar_sync(1 + q, 64);
+            const float other = ot_x[64];
+            const float u = hf == 0 ? part + other : other + part;      // same rounding in both halves
             // model.py:93  score*mask + (1-mask)*NINF
-            const float z = (in_range && st_idx > 0) ? (u0 + u1) : C2V_NINF;
-            if (in_range) a.attention[row] = z;
+            const float z = (in_range && st_idx > 0) ? u : C2V_NINF;
+            if (hf == 0 && in_range) a.attention[row] = z;
 
-            // per-(warp, bag) online-softmax partial -> slot (vtile + bag)
+            // per-(warp, bag) online-softmax partial -> slot (vtile + bag); each half writes its 64 columns
             if (vrow0 < a.N) {
                 const long long vt = vrow0 / tc::VROWS;
                 long long last = vrow0 + tc::VROWS - 1; if (last > a.N - 1) last = a.N - 1;
@@ -328,37 +376,47 @@ encode_tcgen05_kernel(const EncodeArgs a)
                     const bool in_seg = in_range && my_bag == bag;
                     const float m = warp_max(in_seg ? z : -INFINITY);
                     const float e = in_seg ? __expf(z - m) : 0.0f;
-                    const float ssum = warp_sum(e);
                     const size_t slot = (size_t)(vt + bag);
-                    float *pv = a.ws.part_v + slot * tc::H;
+                    float *pv = a.ws.part_v + slot * tc::H + hf * HC;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < HC / 32; ++c) {
                         float t[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) t[j] = e * x[c * 32 + j];
                         butterfly_reduce32(t, lane);
                         pv[c * 32 + lane] = t[0];
                     }
-                    if (lane == 0) { a.ws.part_m[slot] = m; a.ws.part_s[slot] = ssum; }
+                    if (hf == 0) {
+                        const float ssum = warp_sum(e);
+                        if (lane == 0) { a.ws.part_m[slot] = m; a.ws.part_s[slot] = ssum; }
+                    }
                 }
             }
         }
-    } else if (warp < 4 + tc::N_PRODUCER_WARPS) {
+    } else if (warp < tc::MISC_WARP0) {
         // =============================== A PRODUCERS ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-        const int pw = warp - 4;                     // rows 16*pw .. 16*pw+15 of every tile
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int pw = warp - tc::PROD_WARP0;        // rows 8*pw .. 8*pw+7 of every tile
         const int sub_row = lane >> 4;               // which of the 2 rows of a load this lane serves
         const int q = lane & 15;                     // 16-byte column of the 256-byte half row
         const int n_items = my_tiles * tc::NKB;
         const float4 *tab_t = reinterpret_cast<const float4 *>(a.emb_t);
         const float4 *tab_p = reinterpret_cast<const float4 *>(a.emb_p);
+        // smem byte offset of this lane's 8-byte store inside a [128 x 64] fp16 SW128 tile, per load j
+        uint32_t st_off[tc::LDG_PER_ITEM];
+#pragma unroll
+        for (int j = 0; j < tc::LDG_PER_ITEM; ++j) {
+            const int r = pw * tc::ROWS_PER_PW + 2 * j + sub_row;
+            st_off[j] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((q >> 1) ^ (r & 7)) & 7) << 4) + (q & 1) * 8);
+        }
 
         ProducerIdx raw_next = {0, 0, 0};
         uint32_t off_s = 0, off_p = 0, off_e = 0;    // row offsets (float4 units) of the tile being loaded
         auto fetch_idx = [&](int tl) {
             raw_next.s = raw_next.p = raw_next.e = 0;
             if (tl < my_tiles) {
-                const long long row = ((long long)blockIdx.x + (long long)tl * gridDim.x) * tc::ROWS + pw * 16 + q;
+                const long long row = ((long long)blockIdx.x + (long long)tl * gridDim.x) * tc::ROWS +
+                                      pw * tc::ROWS_PER_PW + (lane & (tc::ROWS_PER_PW - 1));
                 if (row < a.N) { raw_next.s = a.starts[row]; raw_next.p = a.paths[row]; raw_next.e = a.ends[row]; }
             }
         };
@@ -368,44 +426,46 @@ encode_tcgen05_kernel(const EncodeArgs a)
             if (s < 0 || s >= a.T) { s = 0; ++bad; }
             if (p < 0 || p >= a.P) { p = 0; ++bad; }
             if (e < 0 || e >= a.T) { e = 0; ++bad; }
-            if (bad && lane < 16) atomicAdd((unsigned long long *)status, (unsigned long long)bad);
+            if (bad && lane < tc::ROWS_PER_PW) atomicAdd((unsigned long long *)status, (unsigned long long)bad);
             off_s = (uint32_t)(s * (tc::E / 4)); off_p = (uint32_t)(p * (tc::E / 4)); off_e = (uint32_t)(e * (tc::E / 4));
         };
-        auto issue = [&](int it, float4 (&buf)[8]) {
+        auto issue = [&](int it, float4 (&buf)[tc::LDG_PER_ITEM]) {
             const int kb = it % tc::NKB;
             const int sub = kb >> 1;                                     // 0 start, 1 path, 2 end (model.py:51)
             const float4 *tab = sub == 1 ? tab_p : tab_t;
             const uint32_t off = sub == 0 ? off_s : (sub == 1 ? off_p : off_e);
             const uint32_t col = (uint32_t)((kb & 1) * 16 + q);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < tc::LDG_PER_ITEM; ++j) {
                 const uint32_t o = __shfl_sync(0xffffffffu, off, 2 * j + sub_row);
                 buf[j] = ldg_nc_v4(tab + (size_t)o + col);
             }
         };
-        auto consume = [&](int it, float4 (&buf)[8]) {
+        auto consume = [&](int it, float4 (&buf)[tc::LDG_PER_ITEM]) {
             const int stage = it % tc::STAGES;
             const uint32_t phase = (uint32_t)(it / tc::STAGES) & 1u;
             mbar_wait(bar_empty + 8 * stage, phase ^ 1u, status);
             const uint32_t a_hi = base + stage * tc::STAGE_BYTES, a_lo = a_hi + tc::TILE_BYTES;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = pw * 16 + 2 * j + sub_row;
+            for (int j = 0; j < tc::LDG_PER_ITEM; ++j) {
                 const float4 v = buf[j];
                 const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
                 const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                 const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y);
                 const __half2 l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
-                const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((q >> 1) ^ (r & 7)) & 7) << 4) + (q & 1) * 8);
-                sts_v2(a_hi + off, pack_h2(h01), pack_h2(h23));
-                sts_v2(a_lo + off, pack_h2(l01), pack_h2(l23));
+                sts_v2(a_hi + st_off[j], pack_h2(h01), pack_h2(h23));
+                sts_v2(a_lo + st_off[j], pack_h2(l01), pack_h2(l23));
             }
-            fence_proxy_async_smem();       // generic-proxy stores -> visible to the tensor core (async proxy)
+            // The generic->async proxy fence for these stores is issued by the MMA thread after it
+            // acquires the full barrier (release here, acquire there, then fence.proxy.async):
+            // a producer-side fence would be a MEMBAR that also waits for this warp's in-flight
+            // gathers of the next k-block.
+            if (a.flags & 1) fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + 8 * stage);
         };
 
-        float4 bufA[8], bufB[8];
+        float4 bufA[tc::LDG_PER_ITEM], bufB[tc::LDG_PER_ITEM];
         if (n_items > 0) {
             fetch_idx(0);
             adopt_idx();
@@ -425,8 +485,8 @@ encode_tcgen05_kernel(const EncodeArgs a)
             }
         }
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (warp == 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp == tc::MISC_WARP0) {
             // =============================== MMA ISSUER ===============================
             if (lane == 0) {
                 for (int tl = 0; tl < my_tiles; ++tl) {
@@ -440,6 +500,7 @@ encode_tcgen05_kernel(const EncodeArgs a)
                         const int stage = it % tc::STAGES;
                         const uint32_t phase = (uint32_t)(it / tc::STAGES) & 1u;
                         mbar_wait(bar_full + 8 * stage, phase, status);
+                        fence_proxy_async_smem();     // producers' st.shared (generic proxy) -> tensor core (async proxy)
                         tc_fence_after();
                         const uint32_t sa = base + stage * tc::STAGE_BYTES;
 #pragma unroll
@@ -458,7 +519,7 @@ encode_tcgen05_kernel(const EncodeArgs a)
                 }
             }
             __syncwarp();
-        } else if (warp == 13) {
+        } else if (warp == tc::MISC_WARP0 + 1) {
             // =============================== W PRODUCER ===============================
             if (lane == 0) {
                 const uint8_t *img = reinterpret_cast<const uint8_t *>(a.ws.w_hi);
@@ -479,7 +540,7 @@ encode_tcgen05_kernel(const EncodeArgs a)
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 14) {
+    if (warp == tc::MISC_WARP0 + 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tc::TMEM_COLS) : "memory");
     }
@@ -493,16 +554,12 @@ int launch_encode_tcgen05(const EncodeArgs &a, cudaStream_t st)
     C2V_CUDA_OK(cudaFuncSetAttribute(encode_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     int grid = a.n_tiles < sms ? a.n_tiles : sms;
     if (grid < 1) grid = 1;
-    encode_tcgen05_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(a);
+    EncodeArgs b = a;
+    const char *dbg = getenv("C2V_PRODUCER_FENCE");
+    if (dbg && dbg[0] == '1') b.flags |= 1;
+    encode_tcgen05_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(b);
     C2V_LAUNCH_OK("encode_tcgen05_kernel");
     return C2V_OK;
-}
-
-int launch_label_tcgen05(const c2v_dims *, const float *, int, const float *, const float *, float *,
-                         void *, size_t, cudaStream_t)
-{
-    set_error("tcgen05 label GEMM is not built yet");
-    return C2V_EUNSUPPORTED;
 }
 
 }  // namespace c2v

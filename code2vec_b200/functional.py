@@ -40,7 +40,9 @@ def make_params(emb_t, emb_p, W, ln_g, ln_b, attn, w_out=None, b_out=None):
     for t in (emb_t, emb_p, W, ln_g, ln_b, attn, w_out, b_out):
         if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
             raise TypeError("parameters must be contiguous fp32")
-    return Params(_ptr(emb_t), _ptr(emb_p), _ptr(W), _ptr(ln_g), _ptr(ln_b), _ptr(attn), _ptr(w_out), _ptr(b_out))
+    p = Params(_ptr(emb_t), _ptr(emb_p), _ptr(W), _ptr(ln_g), _ptr(ln_b), _ptr(attn), _ptr(w_out), _ptr(b_out))
+    p._keep = (emb_t, emb_p, W, ln_g, ln_b, attn, w_out, b_out)   # the struct holds raw pointers: pin the tensors
+    return p
 
 
 def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False, seed=0, algo=_lib.ALGO_AUTO,

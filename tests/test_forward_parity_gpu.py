@@ -201,3 +201,28 @@ def test_host_buffer_api_matches_device_api():
         assert rc == _lib.C2V_EINDEX
     finally:
         lib.c2v_session_destroy(sess)
+
+
+@pytest.mark.parametrize("B,C,H", [(1, 5, 128), (37, 77, 128), (130, 1000, 128), (1024, 8192, 128), (64, 300, 64), (9, 50, 100)])
+def test_label_logits_tcgen05_vs_ffma_vs_oracle(B, C, H):
+    """model.py:83 on the tensor cores (3-pass fp16 split) against the CUDA-core GEMM and the oracle,
+    incl. ragged tile edges and weights at 'trained' scale."""
+    from oracle import oracle
+    rng = np.random.default_rng(B * 31 + C)
+    cvn = np.tanh(rng.standard_normal((B, H))).astype(np.float32)
+    w = (rng.standard_normal((C, H)) * 0.7).astype(np.float32)
+    bias = (0.3 * rng.standard_normal(C)).astype(np.float32)
+    dims = CF.make_dims(10, 10, C, H, H, H)
+    params = CF.make_params(None, None, None, None, None, None, cuda(w), cuda(bias))
+    ref = oracle.label_logits(cvn, w, bias)
+    tol = 3e-6 * max(1.0, float(np.abs(ref).max()))      # fp32 relative: logits reach +-30 here
+    out_f = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_FFMA).cpu().numpy()
+    assert np.abs(out_f - ref).max() <= tol
+    if H in (64, 128):
+        out_t = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_TCGEN05).cpu().numpy()
+        assert np.abs(out_t - ref).max() <= tol, np.abs(out_t - ref).max()
+        out_a = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_AUTO).cpu().numpy()
+        assert np.array_equal(out_a, out_t)
+    else:
+        with pytest.raises(NotImplementedError):
+            CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_TCGEN05)
