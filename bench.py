@@ -234,12 +234,15 @@ def main():
     st = ctypes.c_void_p(stream.cuda_stream)
     label_algo = _lib.ALGO_FFMA if algo == _lib.ALGO_FFMA else _lib.ALGO_AUTO
 
-    def step(i):
+    REUSE = 0x100   # C2V_FLAG_REUSE_PREP: weights are frozen during the run (inference), as the torch
+                    # module does when the parameters' version counters are unchanged
+
+    def step(i, reuse=REUSE):
         o = (i % nb) * B
         _lib.check(lib.c2v_encode_forward(ctypes.byref(dims), ctypes.byref(params), P(s[o:o + B]), P(pth[o:o + B]),
-                                          P(e[o:o + B]), B, L, None, P(cv), P(att), P(ws), ws_n, algo, st), "encode")
+                                          P(e[o:o + B]), B, L, None, P(cv), P(att), P(ws), ws_n, algo | reuse, st), "encode")
         _lib.check(lib.c2v_label_logits(ctypes.byref(dims), ctypes.byref(params), P(cv), B, P(out), P(wl), wl_n,
-                                        label_algo, st), "label")
+                                        label_algo | reuse, st), "label")
         _lib.check(lib.c2v_loss_argmax(P(out), None, B, C, None, P(am), P(mx), None, st), "argmax")
 
     def barrier():
@@ -252,7 +255,7 @@ def main():
     parity = None
     if rank == 0:
         from oracle import oracle
-        step(0); torch.cuda.synchronize(dev)
+        step(0, reuse=0); torch.cuda.synchronize(dev)     # first call builds the weight images
         nchk = min(B, 32)
         npar = {k: v.cpu().numpy() for k, v in p.items()}
         ro, rc_, ra = oracle.forward(npar, s[:nchk].cpu().numpy(), pth[:nchk].cpu().numpy(), e[:nchk].cpu().numpy(),
@@ -320,7 +323,7 @@ def main():
                 o = (i % hb) * B; k = i & 1
                 _lib.check(lib.c2v_forward_host_async(sess, ctypes.byref(params), P(hs[o:o + B]), P(hp[o:o + B]),
                                                       P(he[o:o + B]), None, B, None, P(hcv[k]), P(hat[k]), P(hpr[k]),
-                                                      P(hsc[k]), algo, ctypes.byref(tick)), "forward_host_async")
+                                                      P(hsc[k]), algo | REUSE, ctypes.byref(tick)), "forward_host_async")
                 pending.append(tick.value)
                 if len(pending) == 2:       # results of step i-1 are consumed while step i is in flight
                     _lib.check(lib.c2v_session_wait(sess, pending.pop(0)), "session_wait")

@@ -156,6 +156,8 @@ int c2v_encode_forward(const c2v_dims *d, const c2v_params *p, const int64_t *st
         set_error("workspace too small: %zu < %zu", workspace_bytes, ws.bytes);
         return C2V_EWORKSPACE;
     }
+    const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;
+    algo &= 0xff;
     bool use_tc;
     if (algo == C2V_ALGO_TCGEN05) {
         if (!tcgen05_shape_ok(d)) {
@@ -189,6 +191,7 @@ int c2v_encode_forward(const c2v_dims *d, const c2v_params *p, const int64_t *st
         a.drop_p = drop->p; a.drop_scale = 1.0f / (1.0f - drop->p); a.seed = drop->seed;
     }
     a.attention = attention;
+    a.flags = 0;
     // rows per softmax partial: 64-row CTA tiles (FFMA) or 32-row epilogue warps (tcgen05)
     ws.tile_rows = use_tc ? 32 : 64;
     const int cta_rows = use_tc ? 128 : 64;
@@ -196,9 +199,10 @@ int c2v_encode_forward(const c2v_dims *d, const c2v_params *p, const int64_t *st
     a.ws = ws;
 
     C2V_CUDA_OK(cudaMemsetAsync(ws.status, 0, 256, st));
-    int rc;
-    rc = use_tc ? launch_split_w_tcgen05(d, p->input_linear, a.ws, st)
-                : launch_transpose_w(p->input_linear, ws.w_t, a.H, a.D, (a.H + 3) / 4 * 4, st);
+    int rc = C2V_OK;
+    if (!reuse_prep)
+        rc = use_tc ? launch_split_w_tcgen05(d, p->input_linear, a.ws, st)
+                    : launch_transpose_w(p->input_linear, ws.w_t, a.H, a.D, (a.H + 3) / 4 * 4, st);
     if (rc != C2V_OK) return rc;
     int slot = -1;
     if (g_prof_on) {
@@ -265,9 +269,11 @@ int c2v_label_logits(const c2v_dims *d, const c2v_params *p, const float *code_v
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int H = d->encode;
     const long long C = d->label_count;
+    const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;
+    algo &= 0xff;
     if (algo == C2V_ALGO_TCGEN05 || (algo == C2V_ALGO_AUTO && label_tcgen05_shape_ok(d))) {
         return launch_label_tcgen05(d, code_vector, B, p->output_weight, p->output_bias, outputs,
-                                    workspace, workspace_bytes, st);
+                                    workspace, workspace_bytes, reuse_prep, st);
     }
     // outputs[b,c] = sum_h cv[b,h] * W_out[c,h] + bias[c]   (model.py:83)
     return launch_sgemm(B, (int)C, H, code_vector, H, 1, p->output_weight, 1, H, p->output_bias,

@@ -214,7 +214,7 @@ size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B)
 }
 
 int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float *Wout, const float *bias,
-                         float *out, void *ws, size_t ws_bytes, cudaStream_t st)
+                         float *out, void *ws, size_t ws_bytes, bool reuse_prep, cudaStream_t st)
 {
     if (!label_tcgen05_shape_ok(d)) {
         set_error("tcgen05 label GEMM needs encode_size 64 or 128 (got %d)", d->encode);
@@ -230,17 +230,20 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
     float *hdr = reinterpret_cast<float *>(p);
     unsigned *mxbits = reinterpret_cast<unsigned *>(p + 256);
     const size_t mt = (size_t)(B + 127) / 128, nt = (size_t)((C + 127) / 128);
-    uint8_t *imgA = p + 1024, *imgB = imgA + mt * nkb * 2 * lt::TILE_BYTES;
+    // W_out image first (reusable across calls while the weights are unchanged), cv image after it
+    uint8_t *imgB = p + 1024, *imgA = imgB + nt * nkb * 2 * lt::TILE_BYTES;
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
-    C2V_CUDA_OK(cudaMemsetAsync(mxbits, 0, 4, st));
-    absmax_kernel<<<sms * 4, 256, 0, st>>>(Wout, C * H, mxbits);
-    C2V_LAUNCH_OK("absmax_kernel");
+    if (!reuse_prep) {
+        C2V_CUDA_OK(cudaMemsetAsync(mxbits, 0, 4, st));
+        absmax_kernel<<<sms * 4, 256, 0, st>>>(Wout, C * H, mxbits);
+        C2V_LAUNCH_OK("absmax_kernel");
+        split_rows_kernel<<<sms * 8, 256, 0, st>>>(Wout, C, H, nkb, mxbits, imgB, hdr);
+        C2V_LAUNCH_OK("split_rows_kernel");
+    }
     split_rows_kernel<<<(unsigned)((mt * 128 * nkb * 16 + 255) / 256), 256, 0, st>>>(cv, B, H, nkb, nullptr, imgA, hdr);
-    C2V_LAUNCH_OK("split_rows_kernel");
-    split_rows_kernel<<<sms * 8, 256, 0, st>>>(Wout, C, H, nkb, mxbits, imgB, hdr);
     C2V_LAUNCH_OK("split_rows_kernel");
 
     const int ops = 2 * nkb * 2 * lt::TILE_BYTES, stg = lt::TM * lt::STAGE_LD * 4;

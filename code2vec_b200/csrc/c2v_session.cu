@@ -26,6 +26,7 @@ struct c2v_session {
         long long *h_status;   // pinned
         cudaEvent_t up_done, run_done, down_done;
         bool busy;
+        bool prepped;          // workspaces hold valid weight images (C2V_FLAG_REUSE_PREP)
         int64_t ticket;
     } slot[2];
     int64_t next_ticket;
@@ -113,16 +114,20 @@ int c2v_forward_host_async(c2v_session *s, const c2v_params *p, const int64_t *s
     C2V_CUDA_OK(cudaEventRecord(q.up_done, s->s_up));
     C2V_CUDA_OK(cudaStreamWaitEvent(s->s_run, q.up_done, 0));
 
+    // weight images are per slot: honour the caller's reuse promise only once this slot has them
+    const int base_algo = algo & 0xff;
+    const int reuse = ((algo & C2V_FLAG_REUSE_PREP) && q.prepped) ? C2V_FLAG_REUSE_PREP : 0;
     int rc = c2v_encode_forward(&s->dims, p, (const int64_t *)d_s, (const int64_t *)d_p,
                                 (const int64_t *)d_e, B, s->L, nullptr, q.d_cv, q.d_att, q.ws_enc,
-                                q.ws_enc_bytes, algo, s->s_run);
+                                q.ws_enc_bytes, base_algo | reuse, s->s_run);
     if (rc != C2V_OK) return rc;
     const bool want_head = outputs || pred_label || pred_score;
     if (want_head) {
         if (!p->output_weight) { set_error("c2v_forward_host: output_weight is NULL"); return C2V_EINVAL; }
         rc = c2v_label_logits(&s->dims, p, q.d_cv, B, q.d_out, q.ws_lab, q.ws_lab_bytes,
-                              algo == C2V_ALGO_FFMA ? C2V_ALGO_FFMA : C2V_ALGO_AUTO, s->s_run);
+                              (base_algo == C2V_ALGO_FFMA ? C2V_ALGO_FFMA : C2V_ALGO_AUTO) | reuse, s->s_run);
         if (rc != C2V_OK) return rc;
+        q.prepped = true;
         if (pred_label || pred_score) {
             rc = c2v_loss_argmax(q.d_out, nullptr, B, s->dims.label_count, nullptr,
                                  (int64_t *)q.d_pred, q.d_score, nullptr, s->s_run);
@@ -139,8 +144,8 @@ int c2v_forward_host_async(c2v_session *s, const c2v_params *p, const int64_t *s
     if (pred_score) C2V_CUDA_OK(cudaMemcpyAsync(pred_score, q.d_score, (size_t)B * 4, cudaMemcpyDeviceToHost, s->s_down));
     C2V_CUDA_OK(cudaMemcpyAsync(q.h_status, q.ws_enc, 8, cudaMemcpyDeviceToHost, s->s_down));
     C2V_CUDA_OK(cudaEventRecord(q.down_done, s->s_down));
-    // the next upload into this slot's d_idx must not overtake this batch's kernels
-    C2V_CUDA_OK(cudaStreamWaitEvent(s->s_up, q.run_done, 0));
+    // (the next upload into this slot's d_idx happens two batches later, after the host has
+    //  waited on down_done above, so it cannot overtake this batch's kernels)
     q.busy = true;
     q.ticket = t;
     s->next_ticket = t + 1;

@@ -45,8 +45,28 @@ def make_params(emb_t, emb_p, W, ln_g, ln_b, attn, w_out=None, b_out=None):
     return p
 
 
+REUSE_PREP = 0x100
+
+
+class PrepCache:
+    """A persistent workspace whose derived weight images (split / transposed copies of a weight
+    matrix) are rebuilt only when the weight changed: keyed on (data_ptr, _version, size)."""
+
+    def __init__(self):
+        self.buf, self.key = None, None
+
+    def get(self, nbytes, device, weight):
+        key = (weight.data_ptr(), weight._version, str(device))
+        fresh = self.buf is None or self.buf.numel() < nbytes or self.buf.device != device
+        if fresh:
+            self.buf = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        reuse = (not fresh) and key == self.key
+        self.key = key
+        return self.buf, reuse
+
+
 def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False, seed=0, algo=_lib.ALGO_AUTO,
-                   check_indices=False):
+                   check_indices=False, cache=None, weight=None):
     """-> (code_vector [B,H], attention [B,L]); model.py:48-69 + 90-96."""
     lib = _lib.load()
     _need_cuda(starts, paths, ends)
@@ -57,10 +77,15 @@ def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False
         cv = torch.empty((B, dims.encode), dtype=torch.float32, device=dev)
         att = torch.empty((B, L), dtype=torch.float32, device=dev)
         nbytes = lib.c2v_encode_workspace_bytes(ctypes.byref(dims), B, L)
-        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        if cache is not None and weight is not None:
+            ws, reuse = cache.get(nbytes, dev, weight)
+            if reuse:
+                algo = int(algo) | REUSE_PREP
+        else:
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         drop = Dropout(float(drop_p), 1 if training else 0, int(seed))
         rc = lib.c2v_encode_forward(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
-                                    B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(ws), nbytes, int(algo),
+                                    B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(ws), ws.numel(), int(algo),
                                     _stream(dev))
         _lib.check(rc, "c2v_encode_forward")
         if check_indices:
@@ -72,7 +97,7 @@ def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False
     return cv, att
 
 
-def label_logits(dims, params, cv, algo=_lib.ALGO_AUTO):
+def label_logits(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weight=None):
     """model.py:83"""
     lib = _lib.load()
     _need_cuda(cv)
@@ -81,9 +106,14 @@ def label_logits(dims, params, cv, algo=_lib.ALGO_AUTO):
     with torch.cuda.device(dev):
         out = torch.empty((B, dims.label_count), dtype=torch.float32, device=dev)
         nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
-        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        if cache is not None and weight is not None:
+            ws, reuse = cache.get(nbytes, dev, weight)
+            if reuse:
+                algo = int(algo) | REUSE_PREP
+        else:
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         rc = lib.c2v_label_logits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), B, _ptr(out),
-                                  _ptr(ws), nbytes, int(algo), _stream(dev))
+                                  _ptr(ws), ws.numel(), int(algo), _stream(dev))
         _lib.check(rc, "c2v_label_logits")
     return out
 

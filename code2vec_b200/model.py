@@ -32,9 +32,10 @@ class _EncodeFn(torch.autograd.Function):
     """gathers -> concat -> input_linear -> LayerNorm -> tanh -> dropout -> attention -> code vector."""
 
     @staticmethod
-    def forward(ctx, emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, dims, drop_p, training, seed, algo):
+    def forward(ctx, emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, dims, drop_p, training, seed, algo, cache):
         params = CF.make_params(emb_t, emb_p, W, ln_g, ln_b, attn)
-        cv, att = CF.encode_forward(dims, params, starts, paths, ends, drop_p, training, seed, algo)
+        cv, att = CF.encode_forward(dims, params, starts, paths, ends, drop_p, training, seed, algo,
+                                    cache=cache, weight=W)
         ctx.save_for_backward(emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, cv, att)
         ctx.cfg = (dims, drop_p, training, seed)
         return cv, att
@@ -50,16 +51,16 @@ class _EncodeFn(torch.autograd.Function):
             d_cv = torch.zeros_like(cv)
         g = CF.encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p, training, seed)
         return (g["terminal_embedding"], g["path_embedding"], g["input_linear"], g["ln_weight"], g["ln_bias"],
-                g["attention"], None, None, None, None, None, None, None, None)
+                g["attention"], None, None, None, None, None, None, None, None, None)
 
 
 class _LabelFn(torch.autograd.Function):
     """outputs = cv . W_out^T + b   (model.py:83)"""
 
     @staticmethod
-    def forward(ctx, cv, w_out, b_out, dims, algo):
+    def forward(ctx, cv, w_out, b_out, dims, algo, cache):
         params = CF.make_params(None, None, None, None, None, None, w_out, b_out)
-        out = CF.label_logits(dims, params, cv, algo)
+        out = CF.label_logits(dims, params, cv, algo, cache=cache, weight=w_out)
         ctx.save_for_backward(cv, w_out)
         ctx.dims = dims
         return out
@@ -70,7 +71,7 @@ class _LabelFn(torch.autograd.Function):
         params = CF.make_params(None, None, None, None, None, None, w_out, None)
         d_cv, d_w, d_b = CF.label_backward(ctx.dims, params, cv, d_out, ctx.needs_input_grad[0],
                                            ctx.needs_input_grad[1], ctx.needs_input_grad[2])
-        return d_cv, d_w, d_b, None, None
+        return d_cv, d_w, d_b, None, None, None
 
 
 class Code2Vec(nn.Module):
@@ -105,6 +106,10 @@ class Code2Vec(nn.Module):
 
         self.algo = {"auto": _lib.ALGO_AUTO, "ffma": _lib.ALGO_FFMA, "tcgen05": _lib.ALGO_TCGEN05}[algo]
         self._dropout_calls = 0
+        # persistent workspaces: the hi/lo split images of input_linear / output_linear are rebuilt
+        # only when the optimizer changed the weights (tracked by the tensors' version counters)
+        self._enc_cache = CF.PrepCache()
+        self._lab_cache = CF.PrepCache()
 
     # -- helpers ---------------------------------------------------------------------------
     def _dims(self):
@@ -129,7 +134,7 @@ class Code2Vec(nn.Module):
         code_vector, attention = _EncodeFn.apply(
             self.terminal_embedding.weight, self.path_embedding.weight, self.input_linear.weight,
             self.input_layer_norm.weight, self.input_layer_norm.bias, self.attention_parameter,
-            starts, paths, ends, dims, drop_p, training, seed, self.algo)
+            starts, paths, ends, dims, drop_p, training, seed, self.algo, self._enc_cache)
 
         if option.angular_margin_loss:
             if torch.is_grad_enabled() and (code_vector.requires_grad or self.output_linear.requires_grad):
@@ -147,7 +152,8 @@ class Code2Vec(nn.Module):
                 outputs = CF.angular_logits(dims, params, code_vector, label, option.angular_margin, option.inverse_temp)
         else:
             outputs = _LabelFn.apply(code_vector, self.output_linear.weight, self.output_linear.bias, dims,
-                                     _lib.ALGO_FFMA if self.algo == _lib.ALGO_FFMA else _lib.ALGO_AUTO)
+                                     _lib.ALGO_FFMA if self.algo == _lib.ALGO_FFMA else _lib.ALGO_AUTO,
+                                     self._lab_cache)
 
         return outputs, code_vector, attention
 

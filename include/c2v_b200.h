@@ -56,6 +56,12 @@ enum {
     C2V_ALGO_TCGEN05 = 2  /* tcgen05.mma kind::f16, 3-pass hi/lo split, fp32-accurate */
 };
 
+/* OR-ed into `algo`: the caller guarantees that the parameters behind this workspace have not
+ * changed since the previous call that used it, so the derived weight images (transposed /
+ * hi-lo split copies of input_linear and output_linear kept in the workspace) are reused
+ * instead of rebuilt.  The torch module sets it from the parameters' version counters. */
+#define C2V_FLAG_REUSE_PREP 0x100
+
 /* Sizes read from the reference's Option (main.py:93-115) by Code2Vec.__init__
  * (model.py:18-42). */
 typedef struct c2v_dims {

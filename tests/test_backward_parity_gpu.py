@@ -1,0 +1,117 @@
+"""-m gpu: backward of the CUDA path (c2v_encode_backward / c2v_label_backward through autograd)
+against (1) the gradients the unmodified reference's autograd produced (tests/golden/grad_*.npz),
+(2) torch-CPU autograd over the pinned restatement for a loss that also uses `attention`,
+(3) the C oracle with the kernel's own dropout mask in training mode."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import golden_names, load_golden
+from gpu_util import cuda, model_from_golden, random_batch, random_params
+from code2vec_b200 import functional as CF
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ["terminal_embedding.weight", "path_embedding.weight", "input_linear.weight", "input_layer_norm.weight",
+        "input_layer_norm.bias", "attention_parameter", "output_linear.weight", "output_linear.bias"]
+
+
+def _tol(ref):
+    return 2e-5 * max(1.0, float(np.abs(ref).max()))      # fp32 sums of O(1e3) atomically-added terms
+
+
+@pytest.mark.parametrize("name", golden_names("grad_"))
+@pytest.mark.parametrize("algo", ["ffma", "auto"])
+def test_gradients_match_reference_autograd(name, algo):
+    rec = load_golden(name)
+    m = model_from_golden(rec, algo=algo).train()         # dropout_prob == 0 in these fixtures
+    out, cv, att = m.forward(cuda(rec["starts"]), cuda(rec["paths"]), cuda(rec["ends"]), cuda(rec["label"]))
+    loss = F.nll_loss(F.log_softmax(out, dim=1), cuda(rec["label"]))       # main.py:251-264
+    assert abs(loss.item() - float(rec["loss"])) <= 1e-5 * max(1.0, abs(float(rec["loss"])))
+    loss.backward()
+    got = dict(m.named_parameters())
+    for k in KEYS:
+        g = got[k].grad.cpu().numpy()
+        assert np.abs(g - rec["grads"][k]).max() <= _tol(rec["grads"][k]), k
+
+
+def test_gradients_with_attention_in_the_loss():
+    from oracle import oracle
+    rng = np.random.default_rng(5)
+    T, P, C, E, H, B, L = 300, 200, 11, 128, 128, 7, 90
+    p = random_params(rng, T, P, C, E, E, H)
+    starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
+    starts[3, :] = 0                                       # all-pad bag: PAD row 0 does get gradient
+    wa = rng.standard_normal((B, L)).astype(np.float32); wc = rng.standard_normal((B, H)).astype(np.float32)
+    # reference gradients: torch-CPU autograd over the pinned restatement
+    tp = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in p.items()}
+    out, cv, att = oracle.torch_forward(tp, torch.from_numpy(starts), torch.from_numpy(paths), torch.from_numpy(ends),
+                                        torch.from_numpy(label))
+    ((att * torch.from_numpy(wa)).sum() + (cv * torch.from_numpy(wc)).sum() + 0.1 * out.square().sum()).backward()
+    rec = {"opt": {"T": T, "P": P, "C": C, "Et": E, "Ep": E, "H": H}, "params": p}
+    m = model_from_golden(rec).train()
+    out2, cv2, att2 = m.forward(cuda(starts), cuda(paths), cuda(ends), cuda(label))
+    ((att2 * cuda(wa)).sum() + (cv2 * cuda(wc)).sum() + 0.1 * out2.square().sum()).backward()
+    got = dict(m.named_parameters())
+    for k in KEYS:
+        ref = tp[k].grad.numpy()
+        assert np.abs(got[k].grad.cpu().numpy() - ref).max() <= _tol(ref), k
+    assert np.abs(got["terminal_embedding.weight"].grad[0].cpu().numpy()).max() > 0
+
+
+def test_training_mode_backward_regenerates_the_same_dropout_mask():
+    from oracle import oracle
+    from philox_ref import dropout_mask
+    rng = np.random.default_rng(9)
+    T, P, C, E, H, B, L = 200, 150, 9, 128, 128, 5, 64
+    p = random_params(rng, T, P, C, E, E, H)
+    starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
+    dims = CF.make_dims(T, P, C, E, E, H)
+    tp = {k: cuda(v) for k, v in p.items()}
+    params = CF.make_params(tp["terminal_embedding.weight"], tp["path_embedding.weight"], tp["input_linear.weight"],
+                            tp["input_layer_norm.weight"], tp["input_layer_norm.bias"], tp["attention_parameter"],
+                            tp["output_linear.weight"], tp["output_linear.bias"])
+    seed, prob = 77, 0.25
+    s, pp, e = cuda(starts), cuda(paths), cuda(ends)
+    cv, att = CF.encode_forward(dims, params, s, pp, e, drop_p=prob, training=True, seed=seed)
+    out = CF.label_logits(dims, params, cv)
+    _, _, _, dout = CF.loss_argmax(out, cuda(label), want_grad=True)
+    d_cv, d_w, d_b = CF.label_backward(dims, params, cv, dout)
+    shapes = {"terminal_embedding": (T, E), "path_embedding": (P, E), "input_linear": (H, 3 * E), "ln_weight": (H,),
+              "ln_bias": (H,), "attention": (H,)}
+    g = CF.encode_backward(dims, params, s, pp, e, cv, att, d_cv, None, shapes, drop_p=prob, training=True, seed=seed)
+    mask = dropout_mask(seed, B * L, H, prob).reshape(B, L, H)
+    ref = oracle.backward(p, starts, paths, ends, dout.cpu().numpy(), dropmask=mask)
+    names = {"terminal_embedding": "terminal_embedding.weight", "path_embedding": "path_embedding.weight",
+             "input_linear": "input_linear.weight", "ln_weight": "input_layer_norm.weight",
+             "ln_bias": "input_layer_norm.bias", "attention": "attention_parameter"}
+    for k, rk in names.items():
+        assert np.abs(g[k].cpu().numpy() - ref[rk]).max() <= _tol(ref[rk]), k
+    assert np.abs(d_w.cpu().numpy() - ref["output_linear.weight"]).max() <= _tol(ref["output_linear.weight"])
+    assert np.abs(d_b.cpu().numpy() - ref["output_linear.bias"]).max() <= _tol(ref["output_linear.bias"])
+
+
+def test_one_adam_step_matches_reference_training_semantics():
+    """main.py:171-175: zero_grad, forward, loss, backward, Adam.step -- parameters after one step equal the
+    torch-CPU restatement's (same init, dropout off)."""
+    from oracle import oracle
+    rec = load_golden("grad_cfg2")
+    m = model_from_golden(rec).train()
+    opt = torch.optim.Adam(m.parameters(), lr=0.01, betas=(0.9, 0.999))
+    s, pth, e, lab = (cuda(rec[k]) for k in ("starts", "paths", "ends", "label"))
+    opt.zero_grad()
+    out, _, _ = m.forward(s, pth, e, lab)
+    F.nll_loss(F.log_softmax(out, dim=1), lab).backward()
+    opt.step()
+    tp = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in rec["params"].items()}
+    ropt = torch.optim.Adam(list(tp.values()), lr=0.01, betas=(0.9, 0.999))
+    out, _, _ = oracle.torch_forward(tp, *(torch.from_numpy(rec[k]) for k in ("starts", "paths", "ends", "label")))
+    F.nll_loss(F.log_softmax(out, dim=1), torch.from_numpy(rec["label"])).backward()
+    ropt.step()
+    sd = m.state_dict()
+    for k in KEYS:
+        # Adam's first step moves every touched weight by ~lr regardless of gradient size, so compare loosely
+        # where the gradient is ~0 and tightly elsewhere
+        d = np.abs(sd[k].cpu().numpy() - tp[k].detach().numpy())
+        assert np.quantile(d, 0.999) <= 2e-4, k
