@@ -1,0 +1,94 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: sharding, the single flat-bucket allreduce,
+and that N ranks on shards of a global batch produce the single-process gradients / parameters."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+import torch.nn.functional as F
+
+from code2vec_b200.distributed import FlatGradBucket, broadcast_parameters, ddp_step, shard_items, shard_range
+
+
+def test_shard_range_partitions_everything():
+    for n in (0, 1, 7, 8, 9, 1000, 14048):
+        for w in (1, 2, 4, 8):
+            r = [shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+class TinyBag(nn.Module):
+    """CPU stand-in with the same call surface (the CUDA module cannot run here): embedding bag + head."""
+
+    def __init__(self):
+        super().__init__()
+        self.emb = nn.Embedding(50, 8)
+        self.lin = nn.Linear(8, 5)
+
+    def forward(self, starts, paths, ends, label):
+        cv = torch.tanh(self.emb(starts) + self.emb(ends)).mean(1)
+        return self.lin(cv), cv, None
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)                       # different init per rank on purpose
+        model = TinyBag()
+        broadcast_parameters(model, src=0)
+        bucket = FlatGradBucket(model.parameters())
+        opt = torch.optim.Adam(model.parameters(), lr=0.01)
+        g = torch.Generator().manual_seed(7)
+        starts = torch.randint(0, 50, (16, 6), generator=g); ends = torch.randint(0, 50, (16, 6), generator=g)
+        label = torch.randint(0, 5, (16,), generator=g)
+        idx = shard_items(list(range(16)))                  # this rank's bags of the global batch
+        loss_fn = lambda out, lab: F.nll_loss(F.log_softmax(out, dim=1), lab)
+        ddp_step(model, opt, bucket, starts[idx], starts[idx], ends[idx], label[idx], loss_fn)
+        bucket.check_views()
+        ret[rank] = {k: v.clone() for k, v in model.state_dict().items()}
+        ret[f"g{rank}"] = bucket.flat.clone()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_single_process_step_on_the_global_batch():
+    world, port = 2, _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    # single-process reference on the whole batch, rank 0's init
+    torch.manual_seed(100)
+    model = TinyBag()
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    g = torch.Generator().manual_seed(7)
+    starts = torch.randint(0, 50, (16, 6), generator=g); ends = torch.randint(0, 50, (16, 6), generator=g)
+    label = torch.randint(0, 5, (16,), generator=g)
+    bucket = FlatGradBucket(model.parameters())
+    bucket.zero()
+    out, _, _ = model.forward(starts, starts, ends, label)
+    F.nll_loss(F.log_softmax(out, dim=1), label).backward()
+    assert torch.allclose(ret["g0"], bucket.flat, atol=1e-6) and torch.allclose(ret["g1"], bucket.flat, atol=1e-6)
+    opt.step()
+    for k, v in model.state_dict().items():
+        assert torch.allclose(ret[0][k], v, atol=1e-6), k
+        assert torch.equal(ret[0][k], ret[1][k]), k         # replicas stay bit-identical
+
+
+def test_bucket_is_one_buffer_and_detects_broken_views():
+    m = TinyBag()
+    b = FlatGradBucket(m.parameters())
+    assert b.numel == sum(p.numel() for p in m.parameters()) and b.nbytes() == 4 * b.numel
+    b.check_views()
+    torch.optim.SGD(m.parameters(), lr=0.1).zero_grad(set_to_none=True)
+    with pytest.raises(RuntimeError):
+        b.check_views()
