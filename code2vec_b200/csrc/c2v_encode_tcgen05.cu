@@ -24,10 +24,9 @@
 //   warp 26     TMEM allocator
 // A 3-stage mbarrier ring carries {A_hi, A_lo, W_hi, W_lo} k-blocks (64 KB per stage);
 // two 128-column TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
-#include <cuda_fp16.h>
 #include <cstdlib>
 
-#include "c2v_common.cuh"
+#include "c2v_tc_epilogue.cuh"
 
 namespace c2v {
 
@@ -64,112 +63,6 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(
 bool tcgen05_shape_ok(const c2v_dims *d)
 {
     return d->terminal_embed == tc::E && d->path_embed == tc::E && d->encode == tc::H;
-}
-
-// ------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Spin on the phase parity; a watchdog turns a protocol bug into a trap instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, long long *status) {
-    uint32_t ok = 0;
-    long long t0 = 0;
-    for (uint32_t spins = 0;; ++spins) {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) break;
-        if ((spins & 0x3ff) == 0x3ff) {
-            const long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) {           // ~2 s: certainly a deadlock
-                status[1] = 0xDEAD0000LL | (long long)(bar & 0xffff);
-                __threadfence();
-                __trap();
-            }
-        }
-    }
-}
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B
-// (stride between 8-row groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
-    uint32_t r[32];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float4 ldg_nc_v4(const float4 *p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
-    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ uint32_t pack_h2(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
-
-// byte offset of fp16 element (row, k) inside a [rows x 64] K-major SWIZZLE_128B tile
-__host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
-}
-
-// In-place transpose-reduce across the 32 lanes of a warp: on entry lane i holds v[0..31]
-// (32 columns of its row); on exit v[0] of lane i is the sum over all 32 lanes of column i.
-// 31 shuffles instead of 32 x 5.
-__device__ __forceinline__ void butterfly_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int j = 0; j < off; ++j) {
-            const float send = upper ? v[j] : v[j + off];
-            const float keep = upper ? v[j + off] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -224,25 +117,6 @@ int launch_split_w_tcgen05(const c2v_dims *d, const float *W, EncodeWorkspace &w
 // ------------------------------------------------------------------------------------
 struct ProducerIdx { long long s, p, e; };
 
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-// tanh(v) given w = 2*log2(e)*v :  1 - 2/(2^w + 1); 2^w = inf -> 1, 2^w = 0 -> -1.  Two MUFU ops,
-// absolute error ~2e-7 (same formula as tanh_accurate, constants folded into gamma/beta).
-__device__ __forceinline__ float tanh_from_scaled(float w) {
-    return fmaf(-2.0f, rcp_approx(ex2_approx(w) + 1.0f), 1.0f);
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 __global__ void __launch_bounds__(tc::THREADS, 1)
 encode_tcgen05_kernel(const EncodeArgs a)
 {
@@ -275,11 +149,7 @@ encode_tcgen05_kernel(const EncodeArgs a)
                      ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)tc::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid < 3 * tc::H) {
-        // LayerNorm affine pre-multiplied by 2*log2(e) so tanh needs no extra multiply
-        const int which = tid / tc::H, c = tid % tc::H;
-        s_vec[tid] = which == 0 ? a.ln_g[c] * tc::TWO_LOG2E : which == 1 ? a.ln_b[c] * tc::TWO_LOG2E : a.attn[c];
-    }
+    tce_fill_vectors(a, s_vec, tid);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -288,111 +158,7 @@ encode_tcgen05_kernel(const EncodeArgs a)
     if (warp < tc::N_EPI_WARPS) {
         // =============================== EPILOGUE ===============================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-        const int q = warp & 3;                 // TMEM lane quarter: rows 32q .. 32q+31 of the tile
-        const int hf = warp >> 2;               // column half: 64*hf .. 64*hf+63
-        constexpr int HC = tc::H / 2;           // 64 columns per thread
-        const float inv_scale = a.ws.prep_hdr[0];
-        const float4 *sG = reinterpret_cast<const float4 *>(s_vec + hf * HC);
-        const float4 *sB = reinterpret_cast<const float4 *>(s_vec + tc::H + hf * HC);
-        const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * tc::H + hf * HC);
-        float *my_x = s_xch + ((q * 2 + hf) * 3) * 32 + lane;          // [3][32] per (quarter, half)
-        const float *ot_x = s_xch + ((q * 2 + (hf ^ 1)) * 3) * 32 + lane;
-        for (int tl = 0; tl < my_tiles; ++tl) {
-            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
-            const int acc = tl & 1;
-            const uint32_t acc_phase = (uint32_t)(tl >> 1) & 1u;
-            const long long vrow0 = (long long)tile * tc::ROWS + q * tc::VROWS;
-            const long long row = vrow0 + lane;
-            const bool in_range = row < a.N;
-            const long long st_idx = in_range ? a.starts[row] : 0;       // model.py:64 mask = starts > 0
-
-            mbar_wait(bar_tfull + 8 * acc, acc_phase, status);
-            tc_fence_after();
-            float x[HC];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * tc::H + hf * HC);
-            tmem_ld32(taddr, x);
-            tmem_ld32(taddr + 32, x + 32);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);           // accumulator is free again
-
-            // LayerNorm (model.py:55-56), two-pass; x is scale * (c . W^T); halves exchanged via smem
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int c = 0; c < HC; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
-            float part = (s0 + s1) + (s2 + s3);
-            my_x[0] = part;
-            named_bar_sync(1 + q, 64);
-            const float mean = (part + ot_x[0]) * (1.0f / tc::H);
-            s0 = s1 = s2 = s3 = 0.f;
-#pragma unroll
-            for (int c = 0; c < HC; c += 4) {
-                const float d0 = x[c] - mean, d1 = x[c + 1] - mean, d2 = x[c + 2] - mean, d3 = x[c + 3] - mean;
-                s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
-            }
-            part = (s0 + s1) + (s2 + s3);
-            my_x[32] = part;
-            named_bar_sync(1 + q, 64);
-            const float var = (part + ot_x[32]) * (1.0f / tc::H) * inv_scale * inv_scale;
-            const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
-            const float shift = -mean * nrm;
-            // tanh (model.py:57), dropout (model.py:60-61), score h.a (model.py:92-93)
-            float u0 = 0.f, u1 = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < HC / 4; ++c4) {
-                const float4 g = sG[c4], b = sB[c4], at = sA[c4];
-                float y0 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 0], nrm, shift), g.x, b.x));
-                float y1 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 1], nrm, shift), g.y, b.y));
-                float y2 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 2], nrm, shift), g.z, b.z));
-                float y3 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 3], nrm, shift), g.w, b.w));
-                if (a.drop_p > 0.0f) {
-                    const uint4 bits = dropout_bits(a.seed, row, hf * (HC / 4) + c4);
-                    y0 *= dropout_mul(bits.x, a.drop_p, a.drop_scale);
-                    y1 *= dropout_mul(bits.y, a.drop_p, a.drop_scale);
-                    y2 *= dropout_mul(bits.z, a.drop_p, a.drop_scale);
-                    y3 *= dropout_mul(bits.w, a.drop_p, a.drop_scale);
-                }
-                x[4 * c4 + 0] = y0; x[4 * c4 + 1] = y1; x[4 * c4 + 2] = y2; x[4 * c4 + 3] = y3;
-                u0 = fmaf(y0, at.x, u0); u1 = fmaf(y1, at.y, u1);
-                u0 = fmaf(y2, at.z, u0); u1 = fmaf(y3, at.w, u1);
-            }
-            part = u0 + u1;
-            my_x[64] = part;
-            named_bar_sync(1 + q, 64);
-            const float other = ot_x[64];
-            const float u = hf == 0 ? part + other : other + part;      // same rounding in both halves
-            // model.py:93  score*mask + (1-mask)*NINF
-            const float z = (in_range && st_idx > 0) ? u : C2V_NINF;
-            if (hf == 0 && in_range) a.attention[row] = z;
-
-            // per-(warp, bag) online-softmax partial -> slot (vtile + bag); each half writes its 64 columns
-            if (vrow0 < a.N) {
-                const long long vt = vrow0 / tc::VROWS;
-                long long last = vrow0 + tc::VROWS - 1; if (last > a.N - 1) last = a.N - 1;
-                const long long bag_lo = vrow0 / a.L, bag_hi = last / a.L;
-                const long long my_bag = row / a.L;
-                for (long long bag = bag_lo; bag <= bag_hi; ++bag) {
-                    const bool in_seg = in_range && my_bag == bag;
-                    const float m = warp_max(in_seg ? z : -INFINITY);
-                    const float e = in_seg ? __expf(z - m) : 0.0f;
-                    const size_t slot = (size_t)(vt + bag);
-                    float *pv = a.ws.part_v + slot * tc::H + hf * HC;
-#pragma unroll
-                    for (int c = 0; c < HC / 32; ++c) {
-                        float t[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) t[j] = e * x[c * 32 + j];
-                        butterfly_reduce32(t, lane);
-                        pv[c * 32 + lane] = t[0];
-                    }
-                    if (hf == 0) {
-                        const float ssum = warp_sum(e);
-                        if (lane == 0) { a.ws.part_m[slot] = m; a.ws.part_s[slot] = ssum; }
-                    }
-                }
-            }
-        }
+        tce_epilogue_loop(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
     } else if (warp < tc::MISC_WARP0) {
         // =============================== A PRODUCERS ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -546,8 +312,18 @@ encode_tcgen05_kernel(const EncodeArgs a)
     }
 }
 
+bool encode_tma_available();
+int launch_encode_tma(const EncodeArgs &a, cudaStream_t st);
+
+// Two tensor-core encode kernels share the numerics and the epilogue: K1b (LDG producers, this file)
+// is the default; K1c (TMA tile::gather4 producers, c2v_encode_tma.cu) is correct but bound by the
+// TMA unit's per-row cost (~113 us vs ~90 us, profiles/README.md) and is kept as the opt-in
+// C2V_ENCODE_KERNEL=tma variant.
 int launch_encode_tcgen05(const EncodeArgs &a, cudaStream_t st)
 {
+    const char *which = getenv("C2V_ENCODE_KERNEL");
+    if (which && which[0] == 't' && encode_tma_available()) return launch_encode_tma(a, st);
+
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

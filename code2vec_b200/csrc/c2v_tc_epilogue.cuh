@@ -1,0 +1,141 @@
+// c2v_tc_epilogue.cuh -- the epilogue role shared by the tcgen05 encode kernels (8 warps):
+// TMEM -> registers, LayerNorm (model.py:55-56), tanh (:57), dropout (:60-61), score and NINF
+// masking (:64, :92-93), per-warp online-softmax partials of the weighted sum (:68-69, :96).
+#pragma once
+#include "c2v_tc_ptx.cuh"
+
+namespace c2v {
+
+namespace tce {
+constexpr int ROWS = 128;     // context rows per tile (UMMA M)
+constexpr int H = 128;        // encode size (UMMA N)
+constexpr int VROWS = 32;     // rows per softmax partial = one TMEM lane quarter
+constexpr int N_EPI_WARPS = 8;
+constexpr float TWO_LOG2E = 2.8853900817779268f;
+constexpr int VEC_BYTES = 3 * H * 4;               // gamma' | beta' | attn
+constexpr int XCH_BYTES = 4 * 2 * 3 * 32 * 4;      // [4 quarters][2 halves][3][32] floats
+}  // namespace tce
+
+// LayerNorm affine pre-multiplied by 2*log2(e) so tanh needs no extra multiply
+__device__ __forceinline__ void tce_fill_vectors(const EncodeArgs &a, float *s_vec, int tid) {
+    if (tid < 3 * tce::H) {
+        const int which = tid / tce::H, c = tid % tce::H;
+        s_vec[tid] = which == 0 ? a.ln_g[c] * tce::TWO_LOG2E : which == 1 ? a.ln_b[c] * tce::TWO_LOG2E : a.attn[c];
+    }
+}
+
+// Runs on warps 0..7 (warp q and q+4 share TMEM lane quarter q and split the 128 columns).
+// tile(tl) = blockIdx.x + tl * gridDim.x; accumulator stage tl & 1 at tmem_base + (tl & 1) * 128.
+__device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_vec, float *s_xch,
+                                                  uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
+                                                  int warp, int lane, int my_tiles, long long *status)
+{
+    namespace tc = tce;
+        const int q = warp & 3;                 // TMEM lane quarter: rows 32q .. 32q+31 of the tile
+        const int hf = warp >> 2;               // column half: 64*hf .. 64*hf+63
+        constexpr int HC = tc::H / 2;           // 64 columns per thread
+        const float inv_scale = a.ws.prep_hdr[0];
+        const float4 *sG = reinterpret_cast<const float4 *>(s_vec + hf * HC);
+        const float4 *sB = reinterpret_cast<const float4 *>(s_vec + tc::H + hf * HC);
+        const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * tc::H + hf * HC);
+        float *my_x = s_xch + ((q * 2 + hf) * 3) * 32 + lane;          // [3][32] per (quarter, half)
+        const float *ot_x = s_xch + ((q * 2 + (hf ^ 1)) * 3) * 32 + lane;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+            const int acc = tl & 1;
+            const uint32_t acc_phase = (uint32_t)(tl >> 1) & 1u;
+            const long long vrow0 = (long long)tile * tc::ROWS + q * tc::VROWS;
+            const long long row = vrow0 + lane;
+            const bool in_range = row < a.N;
+            const long long st_idx = in_range ? a.starts[row] : 0;       // model.py:64 mask = starts > 0
+
+            mbar_wait(bar_tfull + 8 * acc, acc_phase, status);
+            tc_fence_after();
+            float x[HC];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * tc::H + hf * HC);
+            tmem_ld32(taddr, x);
+            tmem_ld32(taddr + 32, x + 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);           // accumulator is free again
+
+            // LayerNorm (model.py:55-56), two-pass; x is scale * (c . W^T); halves exchanged via smem
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < HC; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
+            float part = (s0 + s1) + (s2 + s3);
+            my_x[0] = part;
+            named_bar_sync(1 + q, 64);
+            const float mean = (part + ot_x[0]) * (1.0f / tc::H);
+            s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < HC; c += 4) {
+                const float d0 = x[c] - mean, d1 = x[c + 1] - mean, d2 = x[c + 2] - mean, d3 = x[c + 3] - mean;
+                s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+            }
+            part = (s0 + s1) + (s2 + s3);
+            my_x[32] = part;
+            named_bar_sync(1 + q, 64);
+            const float var = (part + ot_x[32]) * (1.0f / tc::H) * inv_scale * inv_scale;
+            const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
+            const float shift = -mean * nrm;
+            // tanh (model.py:57), dropout (model.py:60-61), score h.a (model.py:92-93)
+            float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < HC / 4; ++c4) {
+                const float4 g = sG[c4], b = sB[c4], at = sA[c4];
+                float y0 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 0], nrm, shift), g.x, b.x));
+                float y1 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 1], nrm, shift), g.y, b.y));
+                float y2 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 2], nrm, shift), g.z, b.z));
+                float y3 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 3], nrm, shift), g.w, b.w));
+                if (a.drop_p > 0.0f) {
+                    const uint4 bits = dropout_bits(a.seed, row, hf * (HC / 4) + c4);
+                    y0 *= dropout_mul(bits.x, a.drop_p, a.drop_scale);
+                    y1 *= dropout_mul(bits.y, a.drop_p, a.drop_scale);
+                    y2 *= dropout_mul(bits.z, a.drop_p, a.drop_scale);
+                    y3 *= dropout_mul(bits.w, a.drop_p, a.drop_scale);
+                }
+                x[4 * c4 + 0] = y0; x[4 * c4 + 1] = y1; x[4 * c4 + 2] = y2; x[4 * c4 + 3] = y3;
+                u0 = fmaf(y0, at.x, u0); u1 = fmaf(y1, at.y, u1);
+                u0 = fmaf(y2, at.z, u0); u1 = fmaf(y3, at.w, u1);
+            }
+            part = u0 + u1;
+            my_x[64] = part;
+            named_bar_sync(1 + q, 64);
+            const float other = ot_x[64];
+            const float u = hf == 0 ? part + other : other + part;      // same rounding in both halves
+            // model.py:93  score*mask + (1-mask)*NINF
+            const float z = (in_range && st_idx > 0) ? u : C2V_NINF;
+            if (hf == 0 && in_range) a.attention[row] = z;
+
+            // per-(warp, bag) online-softmax partial -> slot (vtile + bag); each half writes its 64 columns
+            if (vrow0 < a.N) {
+                const long long vt = vrow0 / tc::VROWS;
+                long long last = vrow0 + tc::VROWS - 1; if (last > a.N - 1) last = a.N - 1;
+                const long long bag_lo = vrow0 / a.L, bag_hi = last / a.L;
+                const long long my_bag = row / a.L;
+                for (long long bag = bag_lo; bag <= bag_hi; ++bag) {
+                    const bool in_seg = in_range && my_bag == bag;
+                    const float m = warp_max(in_seg ? z : -INFINITY);
+                    const float e = in_seg ? __expf(z - m) : 0.0f;
+                    const size_t slot = (size_t)(vt + bag);
+                    float *pv = a.ws.part_v + slot * tc::H + hf * HC;
+#pragma unroll
+                    for (int c = 0; c < HC / 32; ++c) {
+                        float t[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) t[j] = e * x[c * 32 + j];
+                        butterfly_reduce32(t, lane);
+                        pv[c * 32 + lane] = t[0];
+                    }
+                    if (hf == 0) {
+                        const float ssum = warp_sum(e);
+                        if (lane == 0) { a.ws.part_m[slot] = m; a.ws.part_s[slot] = ssum; }
+                    }
+                }
+            }
+        }
+}
+
+}  // namespace c2v
