@@ -260,9 +260,8 @@ def main():
         o = (i % nb) * B
         _lib.check(lib.c2v_encode_forward(ctypes.byref(dims), ctypes.byref(params), P(s[o:o + B]), P(pth[o:o + B]),
                                           P(e[o:o + B]), B, L, None, P(cv), P(att), P(ws), ws_n, algo | reuse, st), "encode")
-        _lib.check(lib.c2v_label_logits(ctypes.byref(dims), ctypes.byref(params), P(cv), B, P(out), P(wl), wl_n,
-                                        label_algo | reuse, st), "label")
-        _lib.check(lib.c2v_loss_argmax(P(out), None, B, C, None, P(am), P(mx), None, st), "argmax")
+        _lib.check(lib.c2v_label_logits_argmax(ctypes.byref(dims), ctypes.byref(params), P(cv), B, P(out), P(am), P(mx),
+                                               P(wl), wl_n, label_algo | reuse, st), "label+argmax")
 
     def barrier():
         torch.cuda.synchronize(dev)

@@ -272,12 +272,34 @@ int c2v_label_logits(const c2v_dims *d, const c2v_params *p, const float *code_v
     const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;
     algo &= 0xff;
     if (algo == C2V_ALGO_TCGEN05 || (algo == C2V_ALGO_AUTO && label_tcgen05_shape_ok(d))) {
-        return launch_label_tcgen05(d, code_vector, B, p->output_weight, p->output_bias, outputs,
-                                    workspace, workspace_bytes, reuse_prep, st);
+        return launch_label_tcgen05(d, code_vector, B, p->output_weight, p->output_bias, outputs, nullptr,
+                                    nullptr, workspace, workspace_bytes, reuse_prep, st);
     }
     // outputs[b,c] = sum_h cv[b,h] * W_out[c,h] + bias[c]   (model.py:83)
     return launch_sgemm(B, (int)C, H, code_vector, H, 1, p->output_weight, 1, H, p->output_bias,
                         outputs, C, false, st);
+}
+
+int c2v_label_logits_argmax(const c2v_dims *d, const c2v_params *p, const float *code_vector, int32_t B,
+                            float *outputs, int64_t *argmax, float *maxval, void *workspace,
+                            size_t workspace_bytes, int32_t algo, void *stream)
+{
+    if (!dims_ok(d)) return C2V_EINVAL;
+    if (!p || !p->output_weight || !code_vector || !outputs || B < 1 || d->label_count < 1) {
+        set_error("c2v_label_logits_argmax: bad argument");
+        return C2V_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;
+    const int base_algo = algo & 0xff;
+    if (base_algo == C2V_ALGO_TCGEN05 || (base_algo == C2V_ALGO_AUTO && label_tcgen05_shape_ok(d)))
+        return launch_label_tcgen05(d, code_vector, B, p->output_weight, p->output_bias, outputs,
+                                    reinterpret_cast<long long *>(argmax), maxval, workspace, workspace_bytes,
+                                    reuse_prep, st);
+    int rc = c2v_label_logits(d, p, code_vector, B, outputs, workspace, workspace_bytes, algo, stream);
+    if (rc != C2V_OK || (!argmax && !maxval)) return rc;
+    return launch_loss_argmax(outputs, nullptr, B, d->label_count, nullptr,
+                              reinterpret_cast<long long *>(argmax), maxval, nullptr, st);
 }
 
 int c2v_angular_logits(const c2v_dims *d, const c2v_params *p, const float *code_vector,

@@ -85,8 +85,8 @@ int launch_sgemm(int M, int N, int K, const float *A, long long a_sm, long long 
                  const float *B, long long b_sk, long long b_sn, const float *bias, float *C,
                  long long c_sm, bool accumulate, cudaStream_t st);
 int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float *Wout,
-                         const float *bias, float *out, void *ws, size_t ws_bytes, bool reuse_prep,
-                         cudaStream_t st);
+                         const float *bias, float *out, long long *argmax, float *maxval, void *ws,
+                         size_t ws_bytes, bool reuse_prep, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------
 // device helpers

@@ -124,15 +124,11 @@ int c2v_forward_host_async(c2v_session *s, const c2v_params *p, const int64_t *s
     const bool want_head = outputs || pred_label || pred_score;
     if (want_head) {
         if (!p->output_weight) { set_error("c2v_forward_host: output_weight is NULL"); return C2V_EINVAL; }
-        rc = c2v_label_logits(&s->dims, p, q.d_cv, B, q.d_out, q.ws_lab, q.ws_lab_bytes,
-                              (base_algo == C2V_ALGO_FFMA ? C2V_ALGO_FFMA : C2V_ALGO_AUTO) | reuse, s->s_run);
+        rc = c2v_label_logits_argmax(&s->dims, p, q.d_cv, B, q.d_out, pred_label ? (int64_t *)q.d_pred : nullptr,
+                                     pred_score ? q.d_score : nullptr, q.ws_lab, q.ws_lab_bytes,
+                                     (base_algo == C2V_ALGO_FFMA ? C2V_ALGO_FFMA : C2V_ALGO_AUTO) | reuse, s->s_run);
         if (rc != C2V_OK) return rc;
         q.prepped = true;
-        if (pred_label || pred_score) {
-            rc = c2v_loss_argmax(q.d_out, nullptr, B, s->dims.label_count, nullptr,
-                                 (int64_t *)q.d_pred, q.d_score, nullptr, s->s_run);
-            if (rc != C2V_OK) return rc;
-        }
     }
     C2V_CUDA_OK(cudaEventRecord(q.run_done, s->s_run));
     C2V_CUDA_OK(cudaStreamWaitEvent(s->s_down, q.run_done, 0));

@@ -118,6 +118,29 @@ def label_logits(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weight=None)
     return out
 
 
+def label_logits_argmax(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weight=None):
+    """model.py:83 + main.py:285 fused -> (outputs [B,C], argmax int64 [B], maxval [B])"""
+    lib = _lib.load()
+    _need_cuda(cv)
+    B = cv.shape[0]
+    dev = cv.device
+    with torch.cuda.device(dev):
+        out = torch.empty((B, dims.label_count), dtype=torch.float32, device=dev)
+        am = torch.empty((B,), dtype=torch.int64, device=dev)
+        mx = torch.empty((B,), dtype=torch.float32, device=dev)
+        nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
+        if cache is not None and weight is not None:
+            ws, reuse = cache.get(nbytes, dev, weight)
+            if reuse:
+                algo = int(algo) | REUSE_PREP
+        else:
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        rc = lib.c2v_label_logits_argmax(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), B, _ptr(out),
+                                         _ptr(am), _ptr(mx), _ptr(ws), ws.numel(), int(algo), _stream(dev))
+        _lib.check(rc, "c2v_label_logits_argmax")
+    return out, am, mx
+
+
 def angular_logits(dims, params, cv, label, margin, inverse_temp):
     """model.py:71-80"""
     lib = _lib.load()

@@ -163,12 +163,13 @@ class Code2Vec(nn.Module):
         """-> (pred_label [b], pred_score [b], code_vector [b,H], attention [b,L])"""
         if self.option.angular_margin_loss:
             raise NotImplementedError("predict() needs the plain label head (the angular head needs labels)")
-        was = self.training
-        self.eval()
-        try:
-            dummy = torch.zeros((starts.shape[0],), dtype=torch.int64, device=starts.device)
-            outputs, code_vector, attention = self.forward(starts, paths, ends, dummy)
-        finally:
-            self.train(was)
-        _, am, mx, _ = CF.loss_argmax(outputs)
+        dims = self._dims()
+        params = CF.make_params(self.terminal_embedding.weight, self.path_embedding.weight, self.input_linear.weight,
+                                self.input_layer_norm.weight, self.input_layer_norm.bias, self.attention_parameter,
+                                self.output_linear.weight, self.output_linear.bias)
+        code_vector, attention = CF.encode_forward(dims, params, starts, paths, ends, algo=self.algo,
+                                                   cache=self._enc_cache, weight=self.input_linear.weight)
+        _, am, mx = CF.label_logits_argmax(dims, params, code_vector,
+                                           _lib.ALGO_FFMA if self.algo == _lib.ALGO_FFMA else _lib.ALGO_AUTO,
+                                           cache=self._lab_cache, weight=self.output_linear.weight)
         return am, mx, code_vector, attention

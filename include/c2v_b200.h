@@ -149,6 +149,12 @@ size_t c2v_label_workspace_bytes(const c2v_dims *d, int32_t B);
 int c2v_label_logits(const c2v_dims *d, const c2v_params *p, const float *code_vector, int32_t B,
                      float *outputs, void *workspace, size_t workspace_bytes, int32_t algo,
                      void *stream);
+/* Label logits + the prediction the reference takes from them (`torch.max(preds, dim=1)`,
+ * main.py:285; first maximum wins) in one call: the argmax pass runs right behind the GEMM while the
+ * [B,C] logits are still in L2.  argmax int64 [B], maxval fp32 [B] (either may be NULL). */
+int c2v_label_logits_argmax(const c2v_dims *d, const c2v_params *p, const float *code_vector, int32_t B,
+                            float *outputs, int64_t *argmax, float *maxval, void *workspace,
+                            size_t workspace_bytes, int32_t algo, void *stream);
 int c2v_angular_logits(const c2v_dims *d, const c2v_params *p, const float *code_vector,
                        const int64_t *label, int32_t B, float margin, float inverse_temp,
                        float *outputs, void *stream);

@@ -226,3 +226,33 @@ def test_label_logits_tcgen05_vs_ffma_vs_oracle(B, C, H):
     else:
         with pytest.raises(NotImplementedError):
             CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_TCGEN05)
+
+
+@pytest.mark.parametrize("B,C", [(1, 5), (37, 77), (1024, 8192), (130, 1000)])
+def test_fused_label_argmax_matches_torch_max(B, C):
+    """main.py:285 folded into the label GEMM epilogue: same logits, first maximum wins, ties included."""
+    rng = np.random.default_rng(B + C)
+    H = 128
+    cvn = np.tanh(rng.standard_normal((B, H))).astype(np.float32)
+    w = (rng.standard_normal((C, H)) * 0.3).astype(np.float32)
+    if C > 3:
+        w[C - 1] = w[1]                    # duplicate class -> exact tie: the lower index must win
+    bias = np.zeros(C, np.float32)
+    dims = CF.make_dims(10, 10, C, H, H, H)
+    params = CF.make_params(None, None, None, None, None, None, cuda(w), cuda(bias))
+    out, am, mx = CF.label_logits_argmax(dims, params, cuda(cvn), algo=_lib.ALGO_AUTO)
+    ref = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_TCGEN05)
+    assert torch.equal(out, ref)
+    tv, ti = torch.max(out, dim=1)
+    assert torch.equal(mx, tv) and torch.equal(am, ti)
+    out2, am2, mx2 = CF.label_logits_argmax(dims, params, cuda(cvn), algo=_lib.ALGO_FFMA)
+    tv2, ti2 = torch.max(out2, dim=1)
+    assert torch.equal(mx2, tv2) and torch.equal(am2, ti2)
+
+
+def test_predict_surface():
+    rec = load_golden("cfg2_small")
+    m = model_from_golden(rec).eval()
+    am, mx, cv, att = m.predict(cuda(rec["starts"]), cuda(rec["paths"]), cuda(rec["ends"]))
+    assert np.array_equal(am.cpu().numpy(), rec["outputs"].argmax(1))
+    assert np.abs(cv.cpu().numpy() - rec["code_vector"]).max() <= EXPECT
