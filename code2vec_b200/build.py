@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libc2v_b200.so")
-SOURCES = ["c2v_api.cu", "c2v_session.cu", "c2v_encode_ffma.cu", "c2v_encode_tcgen05.cu", "c2v_encode_tma.cu", "c2v_label_tcgen05.cu", "c2v_head.cu",
+SOURCES = ["c2v_api.cu", "c2v_session.cu", "c2v_encode_ffma.cu", "c2v_encode_tcgen05.cu", "c2v_encode_tma.cu", "c2v_encode_cpa.cu", "c2v_label_tcgen05.cu", "c2v_head.cu",
            "c2v_backward.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -117,6 +117,7 @@ int launch_split_w_tcgen05(const c2v_dims *d, const float *W, EncodeWorkspace &w
 // ------------------------------------------------------------------------------------
 struct ProducerIdx { long long s, p, e; };
 
+template <bool DROPOUT>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 encode_tcgen05_kernel(const EncodeArgs a)
 {
@@ -158,7 +159,7 @@ encode_tcgen05_kernel(const EncodeArgs a)
     if (warp < tc::N_EPI_WARPS) {
         // =============================== EPILOGUE ===============================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-        tce_epilogue_loop(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
+        tce_epilogue_loop<DROPOUT>(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
     } else if (warp < tc::MISC_WARP0) {
         // =============================== A PRODUCERS ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -314,26 +315,25 @@ encode_tcgen05_kernel(const EncodeArgs a)
 
 bool encode_tma_available();
 int launch_encode_tma(const EncodeArgs &a, cudaStream_t st);
+int launch_encode_cpa(const EncodeArgs &a, cudaStream_t st);
 
-// Two tensor-core encode kernels share the numerics and the epilogue: K1b (LDG producers, this file)
-// is the default; K1c (TMA tile::gather4 producers, c2v_encode_tma.cu) is correct but bound by the
-// TMA unit's per-row cost (~113 us vs ~90 us, profiles/README.md) and is kept as the opt-in
-// C2V_ENCODE_KERNEL=tma variant.
+// Three tensor-core encode kernels share the numerics, the MMA schedule and the epilogue
+// (c2v_tc_epilogue.cuh) and differ in how the gathered fp32 rows reach the fp16 hi/lo operand tiles:
+//   K1d  c2v_encode_cpa.cu      cp.async loaders + converter warps            DEFAULT (92.6 us, robust)
+//   K1b  this file              LDG into registers, convert in the same warp  C2V_ENCODE_KERNEL=ldg
+//                               (92.7 us at best, but swings to 117 us with register allocation)
+//   K1c  c2v_encode_tma.cu      TMA tile::gather4 + converter warps           C2V_ENCODE_KERNEL=tma
+//                               (113 us: bound by the TMA unit's per-row cost)
+// Measurements: profiles/README.md.
 int launch_encode_tcgen05(const EncodeArgs &a, cudaStream_t st)
 {
     const char *which = getenv("C2V_ENCODE_KERNEL");
     if (which && which[0] == 't' && encode_tma_available()) return launch_encode_tma(a, st);
-
-    int dev = 0, sms = 0;
-    C2V_CUDA_OK(cudaGetDevice(&dev));
-    C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    C2V_CUDA_OK(cudaFuncSetAttribute(encode_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    int grid = a.n_tiles < sms ? a.n_tiles : sms;
-    if (grid < 1) grid = 1;
+    if (!(which && which[0] == 'l')) return launch_encode_cpa(a, st);
     EncodeArgs b = a;
     const char *dbg = getenv("C2V_PRODUCER_FENCE");
     if (dbg && dbg[0] == '1') b.flags |= 1;
-    encode_tcgen05_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(b);
+    kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(b);
     C2V_LAUNCH_OK("encode_tcgen05_kernel");
     return C2V_OK;
 }

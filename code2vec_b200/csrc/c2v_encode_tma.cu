@@ -63,6 +63,7 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
     return v;
 }
 
+template <bool DROPOUT>
 __global__ void __launch_bounds__(tm::THREADS, 1)
 encode_tma_kernel(const EncodeArgs a, const __grid_constant__ CUtensorMap map_t, const __grid_constant__ CUtensorMap map_p)
 {
@@ -110,7 +111,7 @@ encode_tma_kernel(const EncodeArgs a, const __grid_constant__ CUtensorMap map_t,
     if (warp < tce::N_EPI_WARPS) {
         // =============================== EPILOGUE ===============================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-        tce_epilogue_loop(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
+        tce_epilogue_loop<DROPOUT>(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
     } else if (warp < tm::MISC_WARP0) {
         // =============================== CONVERTERS ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -311,10 +312,11 @@ int launch_encode_tma(const EncodeArgs &a, cudaStream_t st)
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    C2V_CUDA_OK(cudaFuncSetAttribute(encode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tm::SMEM_BYTES));
+    auto kern = a.drop_p > 0.0f ? encode_tma_kernel<true> : encode_tma_kernel<false>;
+    C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tm::SMEM_BYTES));
     int grid = a.n_tiles < sms ? a.n_tiles : sms;
     if (grid < 1) grid = 1;
-    encode_tma_kernel<<<grid, tm::THREADS, tm::SMEM_BYTES, st>>>(a, map_t, map_p);
+    kern<<<grid, tm::THREADS, tm::SMEM_BYTES, st>>>(a, map_t, map_p);
     C2V_LAUNCH_OK("encode_tma_kernel");
     return C2V_OK;
 }

@@ -5,6 +5,10 @@
 
 #include "c2v_common.cuh"
 
+#ifndef C2V_SPIN_NS
+#define C2V_SPIN_NS 64
+#endif
+
 namespace c2v {
 
 // ------------------------------------------------------------------------------------
@@ -31,6 +35,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, long lo
                      "selp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) break;
+        // a failed try_wait returns within ~100 cycles; 28 warps re-polling flood the MIO queue that the
+        // working warps need for LDS / STS / SHFL / MUFU (stall_mio in profiles/): back off instead
+        __nanosleep(C2V_SPIN_NS);
         if ((spins & 0x3ff) == 0x3ff) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
