@@ -313,6 +313,7 @@ encode_tcgen05_kernel(const EncodeArgs a)
     }
 }
 
+
 bool encode_tma_available();
 int launch_encode_tma(const EncodeArgs &a, cudaStream_t st);
 int launch_encode_cpa(const EncodeArgs &a, cudaStream_t st);
@@ -330,6 +331,13 @@ int launch_encode_tcgen05(const EncodeArgs &a, cudaStream_t st)
     const char *which = getenv("C2V_ENCODE_KERNEL");
     if (which && which[0] == 't' && encode_tma_available()) return launch_encode_tma(a, st);
     if (!(which && which[0] == 'l')) return launch_encode_cpa(a, st);
+    int dev = 0, sms = 0;
+    C2V_CUDA_OK(cudaGetDevice(&dev));
+    C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    auto kern = a.drop_p > 0.0f ? encode_tcgen05_kernel<true> : encode_tcgen05_kernel<false>;
+    C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    int grid = a.n_tiles < sms ? a.n_tiles : sms;
+    if (grid < 1) grid = 1;
     EncodeArgs b = a;
     const char *dbg = getenv("C2V_PRODUCER_FENCE");
     if (dbg && dbg[0] == '1') b.flags |= 1;
