@@ -317,8 +317,16 @@ def main():
     k_ms = kms.value / max(1, kcnt.value)
     alg_bytes = bytes_per_ctx(w) * B * L
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "encode_tcgen05_kernel" if lib.c2v_encode_supports_tcgen05(ctypes.byref(dims)) and algo != _lib.ALGO_FFMA else "encode_ffma_kernel",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    kvar = {"l": "encode_tcgen05_kernel", "t": "encode_tma_kernel"}.get(os.environ.get("C2V_ENCODE_KERNEL", "c")[:1], "encode_cpa_kernel")
+    traffic = None
+    try:      # DRAM traffic of the dominant kernel from the committed ncu capture (same workload), per launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if tj["kernel"] == kvar and args.workload == "cfg2":
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": kvar if lib.c2v_encode_supports_tcgen05(ctypes.byref(dims)) and algo != _lib.ALGO_FFMA else "encode_ffma_kernel",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "ctx_per_s_kernel_only": B * L / (k_ms * 1e-3) if k_ms > 0 else 0.0}
 
@@ -378,7 +386,7 @@ def main():
         model.load_state_dict(p)
         model = model.to(dev).train()
         bucket = FlatGradBucket(model.parameters())
-        optim = torch.optim.Adam(model.parameters(), lr=0.01, betas=(0.9, 0.999))     # main.py:138 defaults
+        optim = torch.optim.Adam(model.parameters(), lr=0.01, betas=(0.9, 0.999), fused=True)   # main.py:138 (single-kernel impl)
         loss_fn = lambda o_, l_: F.nll_loss(F.log_softmax(o_, dim=1), l_)            # main.py:251-264
         def tstep(i):
             o = (i % nb) * B

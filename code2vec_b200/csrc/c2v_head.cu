@@ -12,17 +12,24 @@ namespace c2v {
 // ------------------------------------------------------------------------------------
 constexpr int GT = 64, GK = 16;
 
+// gridDim.z > 1: split-K, each z-slice handles k_per_split of K and adds its partial tile with atomics
+// (the launcher zero-fills C first unless it accumulates).
 __global__ void __launch_bounds__(256)
 sgemm_kernel(int M, int N, int K, const float *__restrict__ A, long long a_sm, long long a_sk,
              const float *__restrict__ B, long long b_sk, long long b_sn,
-             const float *__restrict__ bias, float *__restrict__ C, long long c_sm, int accumulate)
+             const float *__restrict__ bias, float *__restrict__ C, long long c_sm, int accumulate,
+             int k_per_split)
 {
     __shared__ float As[GK][GT + 4];
     __shared__ float Bs[GK][GT + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += GK) {
+    const int k_begin = blockIdx.z * k_per_split;
+    const int k_end = (k_begin + k_per_split < K) ? k_begin + k_per_split : K;
+    const bool split = gridDim.z > 1;
+    K = k_end;
+    for (int k0 = k_begin; k0 < k_end; k0 += GK) {
         for (int i = tid; i < GT * GK; i += 256) {
             // choose the faster-varying index along the contiguous dimension of each operand
             int am, ak, bk, bn;
@@ -55,9 +62,10 @@ sgemm_kernel(int M, int N, int K, const float *__restrict__ A, long long a_sm, l
         for (int j = 0; j < 4; ++j) {
             const int gn = n0 + tx * 4 + j;
             if (gn >= N) continue;
-            float v = acc[i][j] + (bias ? bias[gn] : 0.0f);
+            float v = acc[i][j] + ((bias && blockIdx.z == 0) ? bias[gn] : 0.0f);
             float *dst = C + gm * c_sm + gn;
-            *dst = accumulate ? *dst + v : v;
+            if (split) atomicAdd(dst, v);
+            else *dst = accumulate ? *dst + v : v;
         }
     }
 }
@@ -67,9 +75,24 @@ int launch_sgemm(int M, int N, int K, const float *A, long long a_sm, long long 
                  bool accumulate, cudaStream_t st)
 {
     if (M <= 0 || N <= 0) return C2V_OK;
-    dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
+    const int gx = (N + GT - 1) / GT, gy = (M + GT - 1) / GT;
+    // few output tiles but a long reduction (d_cv = d_out . W_out: 32 tiles, K = label_count): split K
+    int splits = 1;
+    if (gx * gy < 128 && K >= 1024) {
+        splits = 592 / (gx * gy);
+        if (splits > K / 256) splits = K / 256;
+        if (splits < 1) splits = 1;
+    }
+    int k_per = (K + splits - 1) / splits;
+    k_per = (k_per + GK - 1) / GK * GK;
+    splits = (K + k_per - 1) / k_per;
+    if (splits > 1 && !accumulate) {
+        if (c_sm == N) C2V_CUDA_OK(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st));
+        else C2V_CUDA_OK(cudaMemset2DAsync(C, (size_t)c_sm * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+    }
+    dim3 grid(gx, gy, splits);
     sgemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, a_sm, a_sk, B, b_sk, b_sn, bias, C, c_sm,
-                                       accumulate ? 1 : 0);
+                                       accumulate ? 1 : 0, k_per);
     C2V_LAUNCH_OK("sgemm_kernel");
     return C2V_OK;
 }
