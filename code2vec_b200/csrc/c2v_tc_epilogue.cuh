@@ -10,10 +10,10 @@ namespace tce {
 constexpr int ROWS = 128;     // context rows per tile (UMMA M)
 constexpr int H = 128;        // encode size (UMMA N)
 constexpr int VROWS = 32;     // rows per softmax partial = one TMEM lane quarter
-constexpr int N_EPI_WARPS = 8;
+constexpr int N_EPI_WARPS = 8;             // default: 2 column slices per TMEM lane quarter
 constexpr float TWO_LOG2E = 2.8853900817779268f;
 constexpr int VEC_BYTES = 3 * H * 4;               // gamma' | beta' | attn
-constexpr int XCH_BYTES = 4 * 2 * 3 * 32 * 4;      // [4 quarters][2 halves][3][32] floats
+constexpr int XCH_BYTES = 4 * 4 * 3 * 32 * 4;      // [4 quarters][<=4 slices][3][32] floats
 }  // namespace tce
 
 // LayerNorm affine pre-multiplied by 2*log2(e) so tanh needs no extra multiply
@@ -28,21 +28,30 @@ __device__ __forceinline__ void tce_fill_vectors(const EncodeArgs &a, float *s_v
 // tile(tl) = blockIdx.x + tl * gridDim.x; accumulator stage tl & 1 at tmem_base + (tl & 1) * 128.
 // DROPOUT is a template parameter so the eval instantiation carries no Philox code: the unrolled epilogue
 // shrinks from ~3000 to ~1500 SASS instructions (it was missing the instruction cache, 16 % stall_no_inst).
-template <bool DROPOUT>
+// NS = column slices per lane quarter (epilogue warps = 4 * NS): warp w handles rows of quarter w & 3 and
+// columns [(w >> 2) * H/NS, ...); LayerNorm moments and the score are summed across the NS warps of a
+// quarter through smem + a named barrier, always in slice order so every warp gets the same bits.
+template <bool DROPOUT, int NS = 2>
 __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_vec, float *s_xch,
                                                   uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
                                                   int warp, int lane, int my_tiles, long long *status)
 {
     namespace tc = tce;
         const int q = warp & 3;                 // TMEM lane quarter: rows 32q .. 32q+31 of the tile
-        const int hf = warp >> 2;               // column half: 64*hf .. 64*hf+63
-        constexpr int HC = tc::H / 2;           // 64 columns per thread
+        const int hf = warp >> 2;               // column slice: HC*hf .. HC*hf+HC-1
+        constexpr int HC = tc::H / NS;          // columns per thread (64 or 32)
         const float inv_scale = a.ws.prep_hdr[0];
         const float4 *sG = reinterpret_cast<const float4 *>(s_vec + hf * HC);
         const float4 *sB = reinterpret_cast<const float4 *>(s_vec + tc::H + hf * HC);
         const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * tc::H + hf * HC);
-        float *my_x = s_xch + ((q * 2 + hf) * 3) * 32 + lane;          // [3][32] per (quarter, half)
-        const float *ot_x = s_xch + ((q * 2 + (hf ^ 1)) * 3) * 32 + lane;
+        float *my_x = s_xch + ((q * NS + hf) * 3) * 32 + lane;          // [3][32] per (quarter, slice)
+        const float *qx = s_xch + (q * NS * 3) * 32 + lane;             // slice s, slot k at qx[(s*3+k)*32]
+        auto xsum = [&](int slot) {
+            float t = 0.0f;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) t += qx[(s * 3 + slot) * 32];
+            return t;
+        };
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
             const int acc = tl & 1;
@@ -56,8 +65,8 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
             tc_fence_after();
             float x[HC];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * tc::H + hf * HC);
-            tmem_ld32(taddr, x);
-            tmem_ld32(taddr + 32, x + 32);
+#pragma unroll
+            for (int c = 0; c < HC / 32; ++c) tmem_ld32(taddr + c * 32, x + c * 32);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -69,8 +78,8 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
             for (int c = 0; c < HC; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
             float part = (s0 + s1) + (s2 + s3);
             my_x[0] = part;
-            named_bar_sync(1 + q, 64);
-            const float mean = (part + ot_x[0]) * (1.0f / tc::H);
+            named_bar_sync(1 + q, 32 * NS);
+            const float mean = xsum(0) * (1.0f / tc::H);
             s0 = s1 = s2 = s3 = 0.f;
 #pragma unroll
             for (int c = 0; c < HC; c += 4) {
@@ -79,8 +88,8 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
             }
             part = (s0 + s1) + (s2 + s3);
             my_x[32] = part;
-            named_bar_sync(1 + q, 64);
-            const float var = (part + ot_x[32]) * (1.0f / tc::H) * inv_scale * inv_scale;
+            named_bar_sync(1 + q, 32 * NS);
+            const float var = xsum(1) * (1.0f / tc::H) * inv_scale * inv_scale;
             const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
             const float shift = -mean * nrm;
             // tanh (model.py:57), dropout (model.py:60-61), score h.a (model.py:92-93)
@@ -105,9 +114,8 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
             }
             part = u0 + u1;
             my_x[64] = part;
-            named_bar_sync(1 + q, 64);
-            const float other = ot_x[64];
-            const float u = hf == 0 ? part + other : other + part;      // same rounding in both halves
+            named_bar_sync(1 + q, 32 * NS);
+            const float u = xsum(2);                                     // same order => same bits in every slice
             // model.py:93  score*mask + (1-mask)*NINF
             const float z = (in_range && st_idx > 0) ? u : C2V_NINF;
             if (hf == 0 && in_range) a.attention[row] = z;
