@@ -59,19 +59,22 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region: started before the warm-up so the
+    process is already looping when the region begins; only samples whose timestamp falls inside
+    [mark_begin, mark_end] count (if the region is shorter than the sampling interval, the nearest sample is
+    reported and flagged)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -79,32 +82,49 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        parsed = []
+        for ts, r in self.rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                parsed.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not parsed:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        t0, t1 = self.t0 or 0.0, self.t1 or 1e18
+        # a row is printed when its query completes; the query itself took a few ms, hence the small slack
+        inside = [p for p in parsed if t0 <= p[0] <= t1 + 0.03]
+        note = None
+        if not inside:
+            mid = 0.5 * (t0 + min(t1, time.time()))
+            inside = [min(parsed, key=lambda p: abs(p[0] - mid))]
+            note = "timed region shorter than the sampling interval: nearest sample"
+        sm = sorted(p[1] for p in inside)
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(p[2] for p in inside),
+               "reasons": sorted({r for p in inside for r in p[3]}), "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def synth_params(w, device, seed=1):
@@ -188,7 +208,7 @@ def run_reference(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -201,7 +221,7 @@ def main():
     w = dict(WORKLOADS[args.workload]); w["name"] = args.workload
 
     if args.impl == "reference":
-        if args.steps == 200:
+        if args.steps == 2000:
             args.steps = 20
         return run_reference(args, w)
 
@@ -285,12 +305,13 @@ def main():
         parity["ok"] = max(parity["max_abs_err"].values()) <= 1e-4
 
     # ---- device-resident throughput ("value") --------------------------------------------------
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler.mark_begin()
     lib.c2v_profile_enable(1)
     l0 = lib.c2v_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -299,6 +320,7 @@ def main():
         step(args.warmup + i)
     ev1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = lib.c2v_launch_count() - l0
     kms, kcnt = ctypes.c_double(0), ctypes.c_int64(0)

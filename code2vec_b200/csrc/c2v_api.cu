@@ -36,7 +36,7 @@ bool label_tcgen05_shape_ok(const c2v_dims *d);
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B);
 
 // ---- profiling hook (c2v_profile_enable / c2v_profile_read) ----------------------------
-static const int kProfRing = 256;
+static const int kProfRing = 4096;
 static bool g_prof_on = false;
 static cudaEvent_t g_prof_ev[kProfRing][2];
 static bool g_prof_made = false;
