@@ -12,6 +12,8 @@
 // smem (197 KB): 2 raw stages [128 rows x 64 fp32] (64 KB) | 2 operand stages {A_hi,A_lo,W_hi,W_lo}
 //                (128 KB) | gamma'/beta'/attn | LN exchange | mbarriers
 
+#include <cstdlib>
+
 #include "c2v_tc_epilogue.cuh"
 
 namespace c2v {
@@ -135,6 +137,7 @@ encode_cpa_kernel(const EncodeArgs a)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_rempty + 8 * st);
                 mbar_wait(bar_oempty + 8 * st, phase ^ 1u, status);       // MMAs of the previous use retired
+                if (!(a.flags & 32))               // (timing experiment: skip the conversion + stores)
 #pragma unroll
                 for (int j = 0; j < ca::LDS_PER_ITEM; ++j) {
                     const __half2 h01 = __floats2half2_rn(v[j].x, v[j].y), h23 = __floats2half2_rn(v[j].z, v[j].w);
@@ -192,6 +195,23 @@ encode_cpa_kernel(const EncodeArgs a)
                     cp_async_cg16(dst + j * 2 * (ca::KB * 4), tab + o);
                 }
                 cp_async_mbar_arrive_noinc(bar_rfull + 8 * st);
+                if (!(a.flags & 2)) {
+                    // Only two raw stages (64 KB) can be in flight per SM, which at HBM latency caps the kernel
+                    // (profiles/README.md).  Pull the half rows of item +2 -- the one that cannot be issued yet --
+                    // towards L2 now: this lane's own row, two 128-B lines.
+                    const char *pf;
+                    if (kb + 2 < ca::NKB) {
+                        const int sub2 = (kb + 2) >> 1;
+                        pf = (sub2 == 1 ? reinterpret_cast<const char *>(a.emb_p) : reinterpret_cast<const char *>(a.emb_t)) +
+                             (sub2 == 0 ? off_s : (sub2 == 1 ? off_p : off_e)) + (kb & 1) * (ca::KB * 4);
+                    } else {                                   // first sub-vector (starts) of the next tile
+                        long long r2 = rs;
+                        if (r2 < 0 || r2 >= a.T) r2 = 0;
+                        pf = reinterpret_cast<const char *>(a.emb_t) + r2 * (ca::E * 4) + (kb & 1) * (ca::KB * 4);
+                    }
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128));
+                }
             }
         }
     } else {
@@ -219,8 +239,8 @@ encode_cpa_kernel(const EncodeArgs a)
                             const uint64_t w_hi = umma_desc(sa + 2 * ca::TILE_BYTES + k * 32);
                             const uint64_t w_lo = umma_desc(sa + 3 * ca::TILE_BYTES + k * 32);
                             umma_f16(d_tmem, a_hi, w_hi, ca::IDESC, (kb | k) != 0 ? 1u : 0u);
-                            umma_f16(d_tmem, a_lo, w_hi, ca::IDESC, 1u);
-                            umma_f16(d_tmem, a_hi, w_lo, ca::IDESC, 1u);
+                            if (!(a.flags & 4)) umma_f16(d_tmem, a_lo, w_hi, ca::IDESC, 1u);
+                            if (!(a.flags & 8)) umma_f16(d_tmem, a_hi, w_lo, ca::IDESC, 1u);
                         }
                         umma_commit(bar_oempty + 8 * st);
                     }
@@ -261,10 +281,13 @@ int launch_encode_cpa(const EncodeArgs &a, cudaStream_t st)
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     auto kern = a.drop_p > 0.0f ? encode_cpa_kernel<true> : encode_cpa_kernel<false>;
+    EncodeArgs b = a;
+    const char *dbg = getenv("C2V_DEBUG_FLAGS");      // timing experiments only (results become wrong)
+    if (dbg) b.flags |= atoi(dbg);
     C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ca::SMEM_BYTES));
     int grid = a.n_tiles < sms ? a.n_tiles : sms;
     if (grid < 1) grid = 1;
-    kern<<<grid, ca::THREADS, ca::SMEM_BYTES, st>>>(a);
+    kern<<<grid, ca::THREADS, ca::SMEM_BYTES, st>>>(b);
     C2V_LAUNCH_OK("encode_cpa_kernel");
     return C2V_OK;
 }

@@ -71,6 +71,7 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);           // accumulator is free again
+            if (a.flags & 16) continue;        // timing experiment: producer side alone (results are wrong)
 
             // LayerNorm (model.py:55-56), two-pass; x is scale * (c . W^T); halves exchanged via smem
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
