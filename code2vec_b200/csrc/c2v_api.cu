@@ -199,6 +199,10 @@ int c2v_encode_forward(const c2v_dims *d, const c2v_params *p, const int64_t *st
     a.ws = ws;
 
     C2V_CUDA_OK(cudaMemsetAsync(ws.status, 0, 256, st));
+#ifdef TM_INSTRUMENT
+    C2V_CUDA_OK(cudaMemsetAsync(ws.status + 16, 0x7f, 8, st));   // min-reduced slots of the instrumented build
+    C2V_CUDA_OK(cudaMemsetAsync(ws.status + 20, 0x7f, 8, st));
+#endif
     int rc = C2V_OK;
     if (!reuse_prep)
         rc = use_tc ? launch_split_w_tcgen05(d, p->input_linear, a.ws, st)

@@ -25,6 +25,7 @@
 // A 3-stage mbarrier ring carries {A_hi, A_lo, W_hi, W_lo} k-blocks (64 KB per stage);
 // two 128-column TMEM accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cstdlib>
+#include <cstring>
 
 #include "c2v_tc_epilogue.cuh"
 
@@ -317,10 +318,12 @@ encode_tcgen05_kernel(const EncodeArgs a)
 bool encode_tma_available();
 int launch_encode_tma(const EncodeArgs &a, cudaStream_t st);
 int launch_encode_cpa(const EncodeArgs &a, cudaStream_t st);
+int launch_encode_tm(const EncodeArgs &a, cudaStream_t st);
 
-// Three tensor-core encode kernels share the numerics, the MMA schedule and the epilogue
-// (c2v_tc_epilogue.cuh) and differ in how the gathered fp32 rows reach the fp16 hi/lo operand tiles:
-//   K1d  c2v_encode_cpa.cu      cp.async loaders + converter warps            DEFAULT (92.6 us, robust)
+// Four tensor-core encode kernels share the numerics, the MMA schedule and the epilogue
+// (c2v_tc_epilogue.cuh) and differ in how the gathered fp32 rows reach the fp16 hi/lo operand:
+//   K1e  c2v_encode_tm.cu       cp.async loaders + converters, A operand in TMEM   DEFAULT
+//   K1d  c2v_encode_cpa.cu      cp.async loaders + converters, A operand in smem   C2V_ENCODE_KERNEL=cpa (92.6 us)
 //   K1b  this file              LDG into registers, convert in the same warp  C2V_ENCODE_KERNEL=ldg
 //                               (92.7 us at best, but swings to 117 us with register allocation)
 //   K1c  c2v_encode_tma.cu      TMA tile::gather4 + converter warps           C2V_ENCODE_KERNEL=tma
@@ -329,8 +332,9 @@ int launch_encode_cpa(const EncodeArgs &a, cudaStream_t st);
 int launch_encode_tcgen05(const EncodeArgs &a, cudaStream_t st)
 {
     const char *which = getenv("C2V_ENCODE_KERNEL");
-    if (which && which[0] == 't' && encode_tma_available()) return launch_encode_tma(a, st);
-    if (!(which && which[0] == 'l')) return launch_encode_cpa(a, st);
+    if (which && !strcmp(which, "tma") && encode_tma_available()) return launch_encode_tma(a, st);
+    if (which && !strcmp(which, "cpa")) return launch_encode_cpa(a, st);
+    if (!(which && !strcmp(which, "ldg"))) return launch_encode_tm(a, st);
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -1,0 +1,349 @@
+// c2v_encode_tm.cu -- K1e: fused gather + encode + attention, activations operand in TENSOR MEMORY.
+//
+// Same numerics / epilogue as K1b-K1d (model.py:48-69 + 90-96; 3-pass fp16 split, c2v_encode_tcgen05.cu), but the
+// gathered-and-split A operand never goes back to shared memory: the converter warps write the fp16 hi/lo
+// halves straight into TMEM with tcgen05.st and the MMAs read A from TMEM (tcgen05.mma [d], [a_tmem], b_desc).
+// Why (profiles/README.md, K1d): K1d moved 224 KB through shared memory per k-block (cp.async 32 + LDS 32 +
+// STS 32 + W copy 32 + MMA operand reads 96) = ~60 us per cfg2 batch at 128 B/clk, and its two 32 KB raw stages
+// kept only 64 KB of gathers in flight per SM (loaders alone: 69 us).  Here the STS and the MMA's A reads are
+// gone (144 KB per k-block) and the 64 KB of smem they occupied became two more raw stages (128 KB in flight).
+//
+// Warps (24):  0-7 epilogue | 8-15 converters | 16-19 loaders | 20 MMA issuer | 21 W producer | 22 TMEM alloc
+// smem (201 KB): 4 raw stages [128 rows x 64 fp32], 16-B chunks XOR-swizzled by (row & 7) (128 KB) |
+//                2 W stages {W_hi, W_lo} K-major SWIZZLE_128B (64 KB) | gamma'/beta'/attn | LN exchange | mbarriers
+// TMEM (512 columns): 2 accumulators [128 lanes x 128 fp32] | 4 A stages {hi: 32 columns, lo: 32 columns},
+//                one 32-bit column = two consecutive k of one context row (lane)
+
+#include <cstdlib>
+
+#include "c2v_tc_epilogue.cuh"
+
+namespace c2v {
+
+namespace tm {
+constexpr int ROWS = tce::ROWS, H = tce::H, E = 128, D = 3 * E;
+constexpr int KB = 64, NKB = D / KB;                  // 6 k-blocks per tile
+constexpr int RAW_STAGES = 4, W_STAGES = 2, A_STAGES = 4;
+constexpr int RAW_ROW_BYTES = KB * 4;                 // 256 B: half an embedding row
+constexpr int RAW_BYTES = ROWS * RAW_ROW_BYTES;       // 32 KB
+constexpr int TILE_BYTES = ROWS * KB * 2;             // 16 KB fp16 tile
+constexpr int W_KB_BYTES = 2 * TILE_BYTES;            // {hi, lo} of one k-block of W
+constexpr int N_CONV_WARPS = 8;
+constexpr int CONV_WARP0 = tce::N_EPI_WARPS;          // 8 (multiple of 4: warp & 3 is the TMEM lane quarter)
+constexpr int N_LOAD_WARPS = 4;
+constexpr int LOAD_WARP0 = CONV_WARP0 + N_CONV_WARPS; // 16
+constexpr int MISC_WARP0 = LOAD_WARP0 + N_LOAD_WARPS; // 20
+constexpr int THREADS = (MISC_WARP0 + 4) * 32;        // 768
+constexpr int CPA_PER_ITEM = ROWS / N_LOAD_WARPS / 2; // 16 x LDGSTS.128 (two 256-B half rows per instruction)
+constexpr int TMEM_COLS = 512;
+constexpr int A_COL0 = 2 * H;                         // first A-stage column
+constexpr int A_STAGE_COLS = KB;                      // hi: KB/2 columns, lo: KB/2 columns
+constexpr int SMEM_RAW_OFF = 0;
+constexpr int SMEM_W_OFF = RAW_STAGES * RAW_BYTES;
+constexpr int SMEM_VEC_OFF = SMEM_W_OFF + W_STAGES * W_KB_BYTES;
+constexpr int SMEM_XCH_OFF = SMEM_VEC_OFF + tce::VEC_BYTES;
+constexpr int SMEM_BAR_OFF = SMEM_XCH_OFF + tce::XCH_BYTES;
+constexpr int SMEM_BYTES = SMEM_BAR_OFF + 256 + 1024;
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+static_assert((RAW_STAGES & (RAW_STAGES - 1)) == 0 && (A_STAGES & (A_STAGES - 1)) == 0 && W_STAGES == 2, "ring index math");
+static_assert(A_COL0 + A_STAGES * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
+}  // namespace tm
+
+__device__ __forceinline__ void tm_cp_async_cg16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tm_cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 tm_lds_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T : A is [128 lanes x 16 k] fp16, two k per 32-bit column (8 columns)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane (lane = 32 * (warp & 3) + laneid)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// -DTM_INSTRUMENT: CTA 0 accumulates the cycles each role spends in each of its barrier waits and writes them to
+// status[4 + slot] (read back by scripts/time_encode.py): who waits for whom, without a profiler.
+#ifdef TM_INSTRUMENT
+#define TM_WAIT(bar, parity, slot) do { const long long _t0 = clock64(); mbar_wait(bar, parity, status); \
+                                        tm_acc[slot] += clock64() - _t0; } while (0)
+#define TM_REPORT(slot) do { if (blockIdx.x == 0 && lane == 0) status[4 + (slot)] = tm_acc[slot]; } while (0)
+#else
+#define TM_WAIT(bar, parity, slot) mbar_wait(bar, parity, status)
+#define TM_REPORT(slot) do { } while (0)
+#endif
+
+template <bool DROPOUT>
+__global__ void __launch_bounds__(tm::THREADS, 1)
+encode_tm_kernel(const EncodeArgs a)
+{
+#ifdef TM_INSTRUMENT
+    long long tm_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long tm_t_start = clock64();
+    unsigned long long tm_g_start;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm_g_start));
+#endif
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char *smem = smem_raw + (base - raw);
+    float *s_vec = reinterpret_cast<float *>(smem + tm::SMEM_VEC_OFF);
+    float *s_xch = reinterpret_cast<float *>(smem + tm::SMEM_XCH_OFF);
+    const uint32_t bar_base = base + tm::SMEM_BAR_OFF;
+    // 8-byte barriers: raw_full[4] @0, raw_empty[4] @32, a_full[4] @64, a_empty[4] @96, w_full[2] @128,
+    //                  w_empty[2] @144, tmem_full[2] @160, tmem_empty[2] @176, tmem ptr @192
+    const uint32_t bar_rfull = bar_base, bar_rempty = bar_base + 32, bar_afull = bar_base + 64,
+                   bar_aempty = bar_base + 96, bar_wfull = bar_base + 128, bar_wempty = bar_base + 144,
+                   bar_tfull = bar_base + 160, bar_tempty = bar_base + 176;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + tm::SMEM_BAR_OFF + 192);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_items = my_tiles * tm::NKB;
+    long long *status = a.ws.status;
+
+    if (tid == 0) {
+        for (int s = 0; s < tm::RAW_STAGES; ++s) {
+            mbar_init(bar_rfull + 8 * s, tm::N_LOAD_WARPS * 32);
+            mbar_init(bar_rempty + 8 * s, tm::N_CONV_WARPS);
+        }
+        for (int s = 0; s < tm::A_STAGES; ++s) {
+            mbar_init(bar_afull + 8 * s, tm::N_CONV_WARPS);
+            mbar_init(bar_aempty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_wfull + 8 * s, 1);
+            mbar_init(bar_wempty + 8 * s, 1);
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, tce::N_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == tm::MISC_WARP0 + 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)tm::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tce_fill_vectors(a, s_vec, tid);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // item it = tl * NKB + kb.  Raw ring / A ring: stage it & 3, use count it >> 2; W ring: stage it & 1, use it >> 1.
+    if (warp < tce::N_EPI_WARPS) {
+        // =============================== EPILOGUE ===============================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+        tce_epilogue_loop<DROPOUT>(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
+    } else if (warp < tm::LOAD_WARP0) {
+        // =============================== CONVERTERS ===============================
+        // thread = one context row (TMEM lane) x 32 consecutive k of the k-block (8 x LDS.128, conflict-free
+        // through the chunk swizzle) -> 16 hi + 16 lo packed columns -> 2 x tcgen05.st.32x32b.x16
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        const int qd = warp & 3, hf = (warp - tm::CONV_WARP0) >> 2;
+        const int r = qd * 32 + lane;
+        uint32_t ld_off[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ld_off[c] = (uint32_t)(r * tm::RAW_ROW_BYTES + ((8 * hf + (c ^ (r & 7))) << 4));
+        const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(tm::A_COL0 + hf * (tm::KB / 4));
+        for (int it = 0; it < n_items; ++it) {
+            const int st = it & (tm::RAW_STAGES - 1);
+            const uint32_t phase = (uint32_t)(it / tm::RAW_STAGES) & 1u;
+            const uint32_t rawb = base + tm::SMEM_RAW_OFF + st * tm::RAW_BYTES;
+            TM_WAIT(bar_rfull + 8 * st, phase, 1);                 // gathered fp32 rows have landed
+            float4 v[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[c] = (a.flags & 128) ? make_float4(0.f, 0.f, 0.f, 0.f) : tm_lds_v4(rawb + ld_off[c]);
+            // the asm volatile loads above complete in order before this arrive: the raw stage can be
+            // refilled by the next gather while this warp converts out of registers
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_rempty + 8 * st);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const __half2 h01 = __floats2half2_rn(v[c].x, v[c].y), h23 = __floats2half2_rn(v[c].z, v[c].w);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                hi[2 * c] = pack_h2(h01);
+                hi[2 * c + 1] = pack_h2(h23);
+                lo[2 * c] = pack_h2(__floats2half2_rn(v[c].x - f01.x, v[c].y - f01.y));
+                lo[2 * c + 1] = pack_h2(__floats2half2_rn(v[c].z - f23.x, v[c].w - f23.y));
+            }
+            const int as = it & (tm::A_STAGES - 1);
+            const uint32_t aphase = (uint32_t)(it / tm::A_STAGES) & 1u;
+            TM_WAIT(bar_aempty + 8 * as, aphase ^ 1u, 2);          // MMAs of the previous use retired
+            tc_fence_after();
+            if (!(a.flags & 32)) {             // (timing experiment: skip the TMEM stores)
+                tmem_st16(t_lane + as * tm::A_STAGE_COLS, hi);
+                tmem_st16(t_lane + as * tm::A_STAGE_COLS + tm::KB / 2, lo);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_afull + 8 * as);
+        }
+        if (warp == tm::CONV_WARP0) { TM_REPORT(1); TM_REPORT(2); }
+    } else if (warp < tm::MISC_WARP0) {
+        // =============================== LOADERS (cp.async) ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int lw = warp - tm::LOAD_WARP0;        // rows 32*lw .. 32*lw+31 of every tile; lane l owns row 32*lw+l's indices
+        // Instruction j copies rows 32*lw + 2j (lanes 0-15) and 2j+1 (lanes 16-31): 512 contiguous bytes of the raw
+        // stage in lane order (a permuted smem destination falls off the LDGSTS fast path: 177 us instead of 69).
+        // The chunk swizzle is applied on the GLOBAL side instead: the lane that writes chunk position q of row r
+        // fetches chunk q ^ (r & 7) of the embedding row; r & 7 = (2j & 7) | sub, so q ^ (r & 7) = (q ^ sub) ^ (2j & 7).
+        const int sub = lane >> 4, q = lane & 15;
+        const char *tab_t = reinterpret_cast<const char *>(a.emb_t);
+        const char *tab_p = reinterpret_cast<const char *>(a.emb_p);
+        uint32_t qoff[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) qoff[c] = (uint32_t)(((q ^ sub) ^ (2 * c)) << 4);
+        const uint32_t dst_lane = (uint32_t)((lw * 32 + sub) * tm::RAW_ROW_BYTES + q * 16);
+        long long rs = 0, rp = 0, re = 0;            // raw indices of the NEXT tile (prefetched)
+        uint32_t off_s = 0, off_p = 0, off_e = 0;    // byte offsets of this lane's row in the tables
+        auto fetch_idx = [&](int tl) {
+            rs = rp = re = 0;
+            if (tl < my_tiles) {
+                const long long row = ((long long)blockIdx.x + (long long)tl * gridDim.x) * tm::ROWS + lw * 32 + lane;
+                if (row < a.N) { rs = a.starts[row]; rp = a.paths[row]; re = a.ends[row]; }
+            }
+        };
+        auto adopt_idx = [&]() {
+            int bad = 0;
+            if (rs < 0 || rs >= a.T) { rs = 0; ++bad; }
+            if (rp < 0 || rp >= a.P) { rp = 0; ++bad; }
+            if (re < 0 || re >= a.T) { re = 0; ++bad; }
+            if (bad) atomicAdd((unsigned long long *)status, (unsigned long long)bad);
+            off_s = (uint32_t)rs * (tm::E * 4); off_p = (uint32_t)rp * (tm::E * 4); off_e = (uint32_t)re * (tm::E * 4);
+        };
+        fetch_idx(0);
+        int it = 0;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            adopt_idx();
+            fetch_idx(tl + 1);
+#pragma unroll
+            for (int kb = 0; kb < tm::NKB; ++kb, ++it) {
+                const int st = it & (tm::RAW_STAGES - 1), sv = kb >> 1;
+                const uint32_t phase = (uint32_t)(it / tm::RAW_STAGES) & 1u;
+                const char *tab = (sv == 1 ? tab_p : tab_t) + (kb & 1) * tm::RAW_ROW_BYTES;
+                const uint32_t off = sv == 0 ? off_s : (sv == 1 ? off_p : off_e);
+                const uint32_t dst = base + tm::SMEM_RAW_OFF + st * tm::RAW_BYTES + dst_lane;
+                TM_WAIT(bar_rempty + 8 * st, phase ^ 1u, 0);
+#pragma unroll
+                for (int j = 0; j < tm::CPA_PER_ITEM; ++j) {
+                    const uint32_t o = __shfl_sync(0xffffffffu, off, 2 * j + sub);
+                    if (!(a.flags & 64)) tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o + qoff[j & 3]));
+                }
+                tm_cp_async_mbar_arrive_noinc(bar_rfull + 8 * st);
+            }
+        }
+        if (warp == tm::LOAD_WARP0) TM_REPORT(0);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == tm::MISC_WARP0) {
+            // =============================== MMA ISSUER ===============================
+            // The whole warp runs the loop converged and one elected lane issues: inside an `if (lane == 0)` region
+            // ptxas wraps every UTCHMMA in an ELECT / BRA.U.ANY loop and rebuilds the descriptors through R2UR
+            // (~25 instructions per MMA); the issuer thread was then the slowest stage of the pipeline
+            // (TM_INSTRUMENT: it waited only 15 % of the time while converters and loaders waited ~50 %).
+            const uint64_t wdesc0 = umma_desc(base + tm::SMEM_W_OFF);       // stage 0, W_hi, k-step 0
+            const uint32_t ta0 = tmem_base + (uint32_t)tm::A_COL0;
+            int it = 0;
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int acc = tl & 1;
+                const uint32_t acc_phase = (uint32_t)(tl >> 1) & 1u;
+                TM_WAIT(bar_tempty + 8 * acc, acc_phase ^ 1u, 5);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * tm::H);
+#pragma unroll 1
+                for (int kb = 0; kb < tm::NKB; ++kb, ++it) {
+                    const int as = it & (tm::A_STAGES - 1), ws = it & 1;
+                    TM_WAIT(bar_afull + 8 * as, (uint32_t)(it / tm::A_STAGES) & 1u, 3);
+                    TM_WAIT(bar_wfull + 8 * ws, (uint32_t)(it >> 1) & 1u, 4);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t w_hi0 = wdesc0 + (uint64_t)(ws * (tm::W_KB_BYTES >> 4));
+                        const uint32_t ta = ta0 + (uint32_t)(as * tm::A_STAGE_COLS);
+#pragma unroll
+                        for (int k = 0; k < tm::KB / 16; ++k) {
+                            const uint32_t a_hi = ta + k * 8, a_lo = ta + tm::KB / 2 + k * 8;
+                            const uint64_t w_hi = w_hi0 + (uint64_t)(k * 2);                  // + 32 B
+                            const uint64_t w_lo = w_hi + (uint64_t)(tm::TILE_BYTES >> 4);
+                            umma_f16_ts(d_tmem, a_hi, w_hi, tm::IDESC, (kb | k) != 0 ? 1u : 0u);
+                            umma_f16_ts(d_tmem, a_lo, w_hi, tm::IDESC, 1u);
+                            umma_f16_ts(d_tmem, a_hi, w_lo, tm::IDESC, 1u);
+                        }
+                        umma_commit(bar_aempty + 8 * as);
+                        umma_commit(bar_wempty + 8 * ws);
+                        if (kb == tm::NKB - 1) umma_commit(bar_tfull + 8 * acc);
+                    }
+                    __syncwarp();
+                }
+            }
+            TM_REPORT(3); TM_REPORT(4); TM_REPORT(5);
+        } else if (warp == tm::MISC_WARP0 + 1) {
+            // =============================== W PRODUCER ===============================
+            if (lane == 0) {
+                const uint8_t *img = reinterpret_cast<const uint8_t *>(a.ws.w_hi);
+                int kb = 0;
+                for (int it = 0; it < n_items; ++it) {
+                    const int ws = it & 1;
+                    TM_WAIT(bar_wempty + 8 * ws, ((uint32_t)(it >> 1) & 1u) ^ 1u, 6);
+                    mbar_arrive_expect_tx(bar_wfull + 8 * ws, tm::W_KB_BYTES);
+                    bulk_copy_g2s(base + tm::SMEM_W_OFF + ws * tm::W_KB_BYTES, img + (size_t)kb * tm::W_KB_BYTES,
+                                  tm::W_KB_BYTES, bar_wfull + 8 * ws);
+                    if (++kb == tm::NKB) kb = 0;
+                }
+                TM_REPORT(6);
+            }
+            __syncwarp();
+        }
+    }
+
+#ifdef TM_INSTRUMENT
+    if (tid == 0) {                                   // epilogue warp 0 leaves last-ish
+        unsigned long long g_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g_end));
+        if (blockIdx.x == 0) { status[4 + 11] = clock64() - tm_t_start; status[18] = (long long)(g_end - tm_g_start); }
+        atomicMin((unsigned long long *)&status[16], tm_g_start);      // host presets [16] = max, [20] = max
+        atomicMax((unsigned long long *)&status[17], g_end);
+        atomicMax((unsigned long long *)&status[19], g_end - tm_g_start);
+        atomicMin((unsigned long long *)&status[20], g_end - tm_g_start);
+    }
+#endif
+    tc_fence_before();
+    __syncthreads();
+    if (warp == tm::MISC_WARP0 + 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tm::TMEM_COLS) : "memory");
+    }
+}
+
+int launch_encode_tm(const EncodeArgs &a, cudaStream_t st)
+{
+    int dev = 0, sms = 0;
+    C2V_CUDA_OK(cudaGetDevice(&dev));
+    C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    auto kern = a.drop_p > 0.0f ? encode_tm_kernel<true> : encode_tm_kernel<false>;
+    EncodeArgs b = a;
+    const char *dbg = getenv("C2V_DEBUG_FLAGS");      // timing experiments only (results become wrong)
+    if (dbg) b.flags |= atoi(dbg);
+    C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tm::SMEM_BYTES));
+    int grid = a.n_tiles < sms ? a.n_tiles : sms;
+    if (grid < 1) grid = 1;
+    kern<<<grid, tm::THREADS, tm::SMEM_BYTES, st>>>(b);
+    C2V_LAUNCH_OK("encode_tm_kernel");
+    return C2V_OK;
+}
+
+}  // namespace c2v
