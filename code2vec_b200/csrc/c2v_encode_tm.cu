@@ -8,7 +8,8 @@
 // kept only 64 KB of gathers in flight per SM (loaders alone: 69 us).  Here the STS and the MMA's A reads are
 // gone (144 KB per k-block) and the 64 KB of smem they occupied became two more raw stages (128 KB in flight).
 //
-// Warps (24):  0-7 epilogue | 8-15 converters | 16-19 loaders | 20 MMA issuer | 21 W producer | 22 TMEM alloc
+// Warps (24):  0-7 epilogue | 8-15 converters | 16-19 loaders | 20 MMA issuer (+ TMEM alloc) | 21 W producer |
+//              22-23 idle register donors.  Registers (pool 768 x 80): 120 | 72 | 56 | 40 | 40 | 24
 // smem (201 KB): 4 raw stages [128 rows x 64 fp32], 16-B chunks XOR-swizzled by (row & 7) (128 KB) |
 //                2 W stages {W_hi, W_lo} K-major SWIZZLE_128B (64 KB) | gamma'/beta'/attn | LN exchange | mbarriers
 // TMEM (512 columns): 2 accumulators [128 lanes x 128 fp32] | 4 A stages {hi: 32 columns, lo: 32 columns},
@@ -33,7 +34,7 @@ constexpr int CONV_WARP0 = tce::N_EPI_WARPS;          // 8 (multiple of 4: warp 
 constexpr int N_LOAD_WARPS = 4;
 constexpr int LOAD_WARP0 = CONV_WARP0 + N_CONV_WARPS; // 16
 constexpr int MISC_WARP0 = LOAD_WARP0 + N_LOAD_WARPS; // 20
-constexpr int THREADS = (MISC_WARP0 + 4) * 32;        // 768
+constexpr int THREADS = (MISC_WARP0 + 4) * 32;        // 768: warps 22-23 only donate their registers (setmaxnreg pool)
 constexpr int CPA_PER_ITEM = ROWS / N_LOAD_WARPS / 2; // 16 x LDGSTS.128 (two 256-B half rows per instruction)
 constexpr int TMEM_COLS = 512;
 constexpr int A_COL0 = 2 * H;                         // first A-stage column
@@ -72,6 +73,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
                  "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -132,7 +137,7 @@ encode_tm_kernel(const EncodeArgs a)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == tm::MISC_WARP0 + 2) {
+    if (warp == tm::MISC_WARP0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)tm::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -152,7 +157,7 @@ encode_tm_kernel(const EncodeArgs a)
         // =============================== CONVERTERS ===============================
         // thread = one context row (TMEM lane) x 32 consecutive k of the k-block (8 x LDS.128, conflict-free
         // through the chunk swizzle) -> 16 hi + 16 lo packed columns -> 2 x tcgen05.st.32x32b.x16
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         const int qd = warp & 3, hf = (warp - tm::CONV_WARP0) >> 2;
         const int r = qd * 32 + lane;
         uint32_t ld_off[8];
@@ -171,25 +176,33 @@ encode_tm_kernel(const EncodeArgs a)
             // refilled by the next gather while this warp converts out of registers
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_rempty + 8 * st);
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const __half2 h01 = __floats2half2_rn(v[c].x, v[c].y), h23 = __floats2half2_rn(v[c].z, v[c].w);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                hi[2 * c] = pack_h2(h01);
-                hi[2 * c + 1] = pack_h2(h23);
-                lo[2 * c] = pack_h2(__floats2half2_rn(v[c].x - f01.x, v[c].y - f01.y));
-                lo[2 * c + 1] = pack_h2(__floats2half2_rn(v[c].z - f23.x, v[c].w - f23.y));
-            }
             const int as = it & (tm::A_STAGES - 1);
             const uint32_t aphase = (uint32_t)(it / tm::A_STAGES) & 1u;
-            TM_WAIT(bar_aempty + 8 * as, aphase ^ 1u, 2);          // MMAs of the previous use retired
-            tc_fence_after();
-            if (!(a.flags & 32)) {             // (timing experiment: skip the TMEM stores)
-                tmem_st16(t_lane + as * tm::A_STAGE_COLS, hi);
-                tmem_st16(t_lane + as * tm::A_STAGE_COLS + tm::KB / 2, lo);
-                tmem_st_wait();
+            const uint32_t t_st = t_lane + as * tm::A_STAGE_COLS;
+            // two halves of 4 chunks (16 k) each, so that 72 registers are enough
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const float4 x = v[4 * g + cc];
+                    const __half2 h01 = __floats2half2_rn(x.x, x.y), h23 = __floats2half2_rn(x.z, x.w);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    hi[2 * cc] = pack_h2(h01);
+                    hi[2 * cc + 1] = pack_h2(h23);
+                    lo[2 * cc] = pack_h2(__floats2half2_rn(x.x - f01.x, x.y - f01.y));
+                    lo[2 * cc + 1] = pack_h2(__floats2half2_rn(x.z - f23.x, x.w - f23.y));
+                }
+                if (g == 0) {
+                    TM_WAIT(bar_aempty + 8 * as, aphase ^ 1u, 2);          // MMAs of the previous use retired
+                    tc_fence_after();
+                }
+                if (!(a.flags & 32)) {             // (timing experiment: skip the TMEM stores)
+                    tmem_st8(t_st + g * 8, hi);
+                    tmem_st8(t_st + tm::KB / 2 + g * 8, lo);
+                }
             }
+            tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_afull + 8 * as);
@@ -197,7 +210,7 @@ encode_tm_kernel(const EncodeArgs a)
         if (warp == tm::CONV_WARP0) { TM_REPORT(1); TM_REPORT(2); }
     } else if (warp < tm::MISC_WARP0) {
         // =============================== LOADERS (cp.async) ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         const int lw = warp - tm::LOAD_WARP0;        // rows 32*lw .. 32*lw+31 of every tile; lane l owns row 32*lw+l's indices
         // Instruction j copies rows 32*lw + 2j (lanes 0-15) and 2j+1 (lanes 16-31): 512 contiguous bytes of the raw
         // stage in lane order (a permuted smem destination falls off the LDGSTS fast path: 177 us instead of 69).
@@ -232,23 +245,32 @@ encode_tm_kernel(const EncodeArgs a)
         for (int tl = 0; tl < my_tiles; ++tl) {
             adopt_idx();
             fetch_idx(tl + 1);
+            // One sub-vector (start / path / end embedding) = two k-blocks.  The 16 row offsets a lane needs are
+            // fetched with 16 back-to-back shuffles per sub-vector (with 40 registers ptxas chained SHFL -> IADD ->
+            // LDGSTS one at a time and the loaders, ~115 cycles per LDGSTS, paced the whole pipeline).
 #pragma unroll
-            for (int kb = 0; kb < tm::NKB; ++kb, ++it) {
-                const int st = it & (tm::RAW_STAGES - 1), sv = kb >> 1;
-                const uint32_t phase = (uint32_t)(it / tm::RAW_STAGES) & 1u;
-                const char *tab = (sv == 1 ? tab_p : tab_t) + (kb & 1) * tm::RAW_ROW_BYTES;
+            for (int sv = 0; sv < 3; ++sv) {
                 const uint32_t off = sv == 0 ? off_s : (sv == 1 ? off_p : off_e);
-                const uint32_t dst = base + tm::SMEM_RAW_OFF + st * tm::RAW_BYTES + dst_lane;
-                TM_WAIT(bar_rempty + 8 * st, phase ^ 1u, 0);
+                const char *tab = sv == 1 ? tab_p : tab_t;
+                uint32_t o[tm::CPA_PER_ITEM];
 #pragma unroll
-                for (int j = 0; j < tm::CPA_PER_ITEM; ++j) {
-                    const uint32_t o = __shfl_sync(0xffffffffu, off, 2 * j + sub);
-                    if (!(a.flags & 64)) tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o + qoff[j & 3]));
+                for (int j = 0; j < tm::CPA_PER_ITEM; ++j) o[j] = __shfl_sync(0xffffffffu, off, 2 * j + sub) + qoff[j & 3];
+#pragma unroll
+                for (int h = 0; h < 2; ++h, ++it) {
+                    const int st = it & (tm::RAW_STAGES - 1);
+                    const uint32_t phase = (uint32_t)(it / tm::RAW_STAGES) & 1u;
+                    const uint32_t dst = base + tm::SMEM_RAW_OFF + st * tm::RAW_BYTES + dst_lane;
+                    TM_WAIT(bar_rempty + 8 * st, phase ^ 1u, 0);
+#pragma unroll
+                    for (int j = 0; j < tm::CPA_PER_ITEM; ++j)
+                        if (!(a.flags & 64)) tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + h * tm::RAW_ROW_BYTES + o[j]);
+                    tm_cp_async_mbar_arrive_noinc(bar_rfull + 8 * st);
                 }
-                tm_cp_async_mbar_arrive_noinc(bar_rfull + 8 * st);
             }
         }
         if (warp == tm::LOAD_WARP0) TM_REPORT(0);
+    } else if (warp >= tm::MISC_WARP0 + 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == tm::MISC_WARP0) {
@@ -323,7 +345,7 @@ encode_tm_kernel(const EncodeArgs a)
 #endif
     tc_fence_before();
     __syncthreads();
-    if (warp == tm::MISC_WARP0 + 2) {
+    if (warp == tm::MISC_WARP0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tm::TMEM_COLS) : "memory");
     }

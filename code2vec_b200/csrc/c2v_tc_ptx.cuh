@@ -25,19 +25,34 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Spin on the phase parity; a watchdog turns a protocol bug into a trap instead of a hung GPU.
+// Wait for the phase with the given parity; a watchdog turns a protocol bug into a trap instead of a hung GPU.
+// A bare try_wait returns after ~30 cycles, so a waiting warp re-polls ~30x per microsecond: in the K1e profile two
+// thirds of all executed warp instructions were these poll loops, taking issue slots from the warps that had work.
+// Measured alternatives (cfg2, K1e): try_wait with a suspend-time hint of 1 or 20 us: 82.6-83.1 us (the hardware
+// wake-up is slower than a poll); nanosleep 500: 74.1 us; nanosleep 64: 72.9 us  -> wake-up latency matters more than
+// the issue slots the polls take.
+#ifndef C2V_WAIT_HINT_NS
+#define C2V_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, long long *status) {
     uint32_t ok = 0;
     long long t0 = 0;
     for (uint32_t spins = 0;; ++spins) {
+#if C2V_WAIT_HINT_NS > 0
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"((uint32_t)C2V_WAIT_HINT_NS) : "memory");
+#else
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                      "selp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
         if (ok) break;
-        // a failed try_wait returns within ~100 cycles; 28 warps re-polling flood the MIO queue that the
-        // working warps need for LDS / STS / SHFL / MUFU (stall_mio in profiles/): back off instead
+#if C2V_SPIN_NS > 0
         __nanosleep(C2V_SPIN_NS);
+#endif
         if ((spins & 0x3ff) == 0x3ff) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
@@ -49,7 +64,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, long lo
         }
     }
 }
-// one lane of a converged warp (the same lane every time: the lowest one)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
