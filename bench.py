@@ -339,7 +339,8 @@ def main():
     k_ms = kms.value / max(1, kcnt.value)
     alg_bytes = bytes_per_ctx(w) * B * L
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    kvar = {"l": "encode_tcgen05_kernel", "t": "encode_tma_kernel"}.get(os.environ.get("C2V_ENCODE_KERNEL", "c")[:1], "encode_cpa_kernel")
+    kvar = {"ldg": "encode_tcgen05_kernel", "tma": "encode_tma_kernel", "cpa": "encode_cpa_kernel"}.get(
+        os.environ.get("C2V_ENCODE_KERNEL", ""), "encode_tm_kernel")
     traffic = None
     try:      # DRAM traffic of the dominant kernel from the committed ncu capture (same workload), per launch
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))

@@ -61,24 +61,37 @@ constexpr float TWO_LOG2E = 2.8853900817779268f;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 }  // namespace tc
 
+// K1e (c2v_encode_tm.cu) pads every sub-vector to 128 k and the encode size to 128 columns, so it also serves
+// the reference's default 100/100/100 (main.py:56-58): terminal_embed == path_embed = E, E % 4 == 0, E <= 128,
+// encode_size in {100, 128}.  Row offsets are 32-bit inside the kernels: tables up to 4 GB.
 bool tcgen05_shape_ok(const c2v_dims *d)
 {
-    return d->terminal_embed == tc::E && d->path_embed == tc::E && d->encode == tc::H;
+    const int E = d->terminal_embed;
+    if (d->path_embed != E || E < 4 || E > tc::E || (E & 3)) return false;
+    if (d->encode != 100 && d->encode != tc::H) return false;
+    const long long row_bytes = (long long)E * 4;
+    return d->terminal_count * row_bytes < (1ll << 32) && d->path_count * row_bytes < (1ll << 32);
 }
 
 // ------------------------------------------------------------------------------------
-// weight preparation: W [H, D] fp32 -> per k-block {hi tile, lo tile} images in the exact
-// shared-memory layout, scaled by 2^k.  One CTA; 49 K elements.
+// weight preparation: W [H, 3E] fp32 -> 6 k-block images {hi tile, lo tile} of [128 n x 64 k] fp16 in the exact
+// shared-memory layout, scaled by 2^k.  Sub-vector sv (start / path / end) owns k-blocks 2sv, 2sv+1; k >= E and
+// n >= H are zero padding.  One CTA; <= 49 K elements.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__restrict__ hdr)
+split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__restrict__ hdr, int E, int H)
 {
     __shared__ float red[32];
     const int tid = threadIdx.x;
+    const int D = 3 * E;
     float mx = 0.0f;
-    for (int i = tid; i < tc::H * tc::D; i += 1024) mx = fmaxf(mx, fabsf(W[i]));
+    for (int i = tid; i < H * D; i += 1024) mx = fmaxf(mx, fabsf(W[i]));
     mx = warp_max(mx);
     if ((tid & 31) == 0) red[tid >> 5] = mx;
+    if (E < tc::E || H < tc::H) {                            // zero padding of the image
+        uint4 *z = reinterpret_cast<uint4 *>(img);
+        for (int i = tid; i < tc::NKB * tc::W_KB_BYTES / 16; i += 1024) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncthreads();
     mx = red[0];
     for (int i = 1; i < 32; ++i) mx = fmaxf(mx, red[i]);
@@ -92,12 +105,13 @@ split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__
         scale = ldexpf(1.0f, k);
     }
     if (tid == 0) { hdr[0] = 1.0f / scale; hdr[1] = scale; }
-    for (int i = tid; i < tc::H * tc::D; i += 1024) {
-        const int n = i / tc::D, k = i % tc::D;
+    for (int i = tid; i < H * D; i += 1024) {
+        const int n = i / D, k = i % D;
+        const int sv = k / E, e = k % E;
         const float w = W[i] * scale;
         const __half hi = __float2half_rn(w);
         const __half lo = __float2half_rn(w - __half2float(hi));
-        const int kb = k / tc::KB, kk = k % tc::KB;
+        const int kb = 2 * sv + e / tc::KB, kk = e % tc::KB;
         uint8_t *base = img + (size_t)kb * tc::W_KB_BYTES;
         const uint32_t off = sw128_offset(n, kk);
         *reinterpret_cast<__half *>(base + off) = hi;
@@ -107,8 +121,7 @@ split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__
 
 int launch_split_w_tcgen05(const c2v_dims *d, const float *W, EncodeWorkspace &ws, cudaStream_t st)
 {
-    (void)d;
-    split_w_kernel<<<1, 1024, 0, st>>>(W, reinterpret_cast<uint8_t *>(ws.w_hi), ws.prep_hdr);
+    split_w_kernel<<<1, 1024, 0, st>>>(W, reinterpret_cast<uint8_t *>(ws.w_hi), ws.prep_hdr, d->terminal_embed, d->encode);
     C2V_LAUNCH_OK("split_w_kernel");
     return C2V_OK;
 }
@@ -332,6 +345,7 @@ int launch_encode_tm(const EncodeArgs &a, cudaStream_t st);
 int launch_encode_tcgen05(const EncodeArgs &a, cudaStream_t st)
 {
     const char *which = getenv("C2V_ENCODE_KERNEL");
+    if (a.Et != tc::E || a.H != tc::H) which = nullptr;        // the older variants are 128/128/128 only
     if (which && !strcmp(which, "tma") && encode_tma_available()) return launch_encode_tma(a, st);
     if (which && !strcmp(which, "cpa")) return launch_encode_cpa(a, st);
     if (!(which && !strcmp(which, "ldg"))) return launch_encode_tm(a, st);

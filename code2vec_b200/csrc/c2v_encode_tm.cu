@@ -53,6 +53,10 @@ static_assert(A_COL0 + A_STAGES * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
 __device__ __forceinline__ void tm_cp_async_cg16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// src_bytes = 0: nothing is read, the 16 bytes are zero-filled (padding of an embedding size < 128)
+__device__ __forceinline__ void tm_cp_async_cg16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void tm_cp_async_mbar_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -91,7 +95,8 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 #define TM_REPORT(slot) do { } while (0)
 #endif
 
-template <bool DROPOUT>
+// FULL_E: terminal_embed = path_embed = 128 (no padding chunks); HV = encode_size (100 or 128).
+template <bool DROPOUT, bool FULL_E, int HV>
 __global__ void __launch_bounds__(tm::THREADS, 1)
 encode_tm_kernel(const EncodeArgs a)
 {
@@ -152,7 +157,7 @@ encode_tm_kernel(const EncodeArgs a)
     if (warp < tce::N_EPI_WARPS) {
         // =============================== EPILOGUE ===============================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-        tce_epilogue_loop<DROPOUT>(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
+        tce_epilogue_loop<DROPOUT, 2, HV>(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
     } else if (warp < tm::LOAD_WARP0) {
         // =============================== CONVERTERS ===============================
         // thread = one context row (TMEM lane) x 32 consecutive k of the k-block (8 x LDS.128, conflict-free
@@ -223,6 +228,7 @@ encode_tm_kernel(const EncodeArgs a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) qoff[c] = (uint32_t)(((q ^ sub) ^ (2 * c)) << 4);
         const uint32_t dst_lane = (uint32_t)((lw * 32 + sub) * tm::RAW_ROW_BYTES + q * 16);
+        const uint32_t row_bytes = FULL_E ? (uint32_t)(tm::E * 4) : (uint32_t)(a.Et * 4);     // Et == Ep
         long long rs = 0, rp = 0, re = 0;            // raw indices of the NEXT tile (prefetched)
         uint32_t off_s = 0, off_p = 0, off_e = 0;    // byte offsets of this lane's row in the tables
         auto fetch_idx = [&](int tl) {
@@ -238,7 +244,7 @@ encode_tm_kernel(const EncodeArgs a)
             if (rp < 0 || rp >= a.P) { rp = 0; ++bad; }
             if (re < 0 || re >= a.T) { re = 0; ++bad; }
             if (bad) atomicAdd((unsigned long long *)status, (unsigned long long)bad);
-            off_s = (uint32_t)rs * (tm::E * 4); off_p = (uint32_t)rp * (tm::E * 4); off_e = (uint32_t)re * (tm::E * 4);
+            off_s = (uint32_t)rs * row_bytes; off_p = (uint32_t)rp * row_bytes; off_e = (uint32_t)re * row_bytes;
         };
         fetch_idx(0);
         int it = 0;
@@ -254,7 +260,7 @@ encode_tm_kernel(const EncodeArgs a)
                 const char *tab = sv == 1 ? tab_p : tab_t;
                 uint32_t o[tm::CPA_PER_ITEM];
 #pragma unroll
-                for (int j = 0; j < tm::CPA_PER_ITEM; ++j) o[j] = __shfl_sync(0xffffffffu, off, 2 * j + sub) + qoff[j & 3];
+                for (int j = 0; j < tm::CPA_PER_ITEM; ++j) o[j] = __shfl_sync(0xffffffffu, off, 2 * j + sub);
 #pragma unroll
                 for (int h = 0; h < 2; ++h, ++it) {
                     const int st = it & (tm::RAW_STAGES - 1);
@@ -262,8 +268,15 @@ encode_tm_kernel(const EncodeArgs a)
                     const uint32_t dst = base + tm::SMEM_RAW_OFF + st * tm::RAW_BYTES + dst_lane;
                     TM_WAIT(bar_rempty + 8 * st, phase ^ 1u, 0);
 #pragma unroll
-                    for (int j = 0; j < tm::CPA_PER_ITEM; ++j)
-                        if (!(a.flags & 64)) tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + h * tm::RAW_ROW_BYTES + o[j]);
+                    for (int j = 0; j < tm::CPA_PER_ITEM; ++j) {
+                        const uint32_t chunk = (uint32_t)(h * tm::RAW_ROW_BYTES) + qoff[j & 3];   // byte offset in the row
+                        if (FULL_E) {
+                            if (!(a.flags & 64)) tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o[j] + chunk));
+                        } else {        // chunks at or beyond the embedding size are zero-filled, not read
+                            const bool real = chunk < row_bytes;
+                            tm_cp_async_cg16_zfill(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o[j] + (real ? chunk : 0u)), real ? 16u : 0u);
+                        }
+                    }
                     tm_cp_async_mbar_arrive_noinc(bar_rfull + 8 * st);
                 }
             }
@@ -356,7 +369,18 @@ int launch_encode_tm(const EncodeArgs &a, cudaStream_t st)
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    auto kern = a.drop_p > 0.0f ? encode_tm_kernel<true> : encode_tm_kernel<false>;
+    const bool drop = a.drop_p > 0.0f, full = a.Et == tm::E;
+    void (*kern)(const EncodeArgs) = nullptr;
+    if (a.H == 128) {
+        kern = full ? (drop ? encode_tm_kernel<true, true, 128> : encode_tm_kernel<false, true, 128>)
+                    : (drop ? encode_tm_kernel<true, false, 128> : encode_tm_kernel<false, false, 128>);
+    } else if (a.H == 100) {
+        kern = full ? (drop ? encode_tm_kernel<true, true, 100> : encode_tm_kernel<false, true, 100>)
+                    : (drop ? encode_tm_kernel<true, false, 100> : encode_tm_kernel<false, false, 100>);
+    } else {
+        set_error("encode_tm_kernel: encode_size %d not supported (100 or 128)", a.H);
+        return C2V_EUNSUPPORTED;
+    }
     EncodeArgs b = a;
     const char *dbg = getenv("C2V_DEBUG_FLAGS");      // timing experiments only (results become wrong)
     if (dbg) b.flags |= atoi(dbg);

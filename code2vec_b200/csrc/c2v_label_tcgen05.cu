@@ -247,7 +247,8 @@ label_gemm_tcgen05_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__res
     }
 }
 
-bool label_tcgen05_shape_ok(const c2v_dims *d) { return d->encode == 64 || d->encode == 128; }
+// K (= encode_size) is zero-padded to a multiple of 64 inside the operand images
+bool label_tcgen05_shape_ok(const c2v_dims *d) { return d->encode >= 4 && d->encode <= 128 && (d->encode & 3) == 0; }
 
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B)
 {
@@ -267,10 +268,10 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
                          cudaStream_t st)
 {
     if (!label_tcgen05_shape_ok(d)) {
-        set_error("tcgen05 label GEMM needs encode_size 64 or 128 (got %d)", d->encode);
+        set_error("tcgen05 label GEMM needs encode_size %% 4 == 0 and <= 128 (got %d)", d->encode);
         return C2V_EUNSUPPORTED;
     }
-    const int H = d->encode, nkb = H / 64;
+    const int H = d->encode, nkb = (H + 63) / 64;
     const long long C = d->label_count;
     if (!ws || ws_bytes < label_tcgen05_workspace_bytes(d, B)) {
         set_error("label workspace too small: %zu < %zu", ws_bytes, label_tcgen05_workspace_bytes(d, B));

@@ -16,11 +16,111 @@ constexpr int VEC_BYTES = 3 * H * 4;               // gamma' | beta' | attn
 constexpr int XCH_BYTES = 4 * 4 * 3 * 32 * 4;      // [4 quarters][<=4 slices][3][32] floats
 }  // namespace tce
 
-// LayerNorm affine pre-multiplied by 2*log2(e) so tanh needs no extra multiply
+// LayerNorm affine pre-multiplied by 2*log2(e) so tanh needs no extra multiply; columns >= a.H (padding of the
+// 128-wide tile when encode_size < 128) get gamma' = beta' = attn = 0
 __device__ __forceinline__ void tce_fill_vectors(const EncodeArgs &a, float *s_vec, int tid) {
     if (tid < 3 * tce::H) {
         const int which = tid / tce::H, c = tid % tce::H;
-        s_vec[tid] = which == 0 ? a.ln_g[c] * tce::TWO_LOG2E : which == 1 ? a.ln_b[c] * tce::TWO_LOG2E : a.attn[c];
+        float v = 0.0f;
+        if (c < a.H) v = which == 0 ? a.ln_g[c] * tce::TWO_LOG2E : which == 1 ? a.ln_b[c] * tce::TWO_LOG2E : a.attn[c];
+        s_vec[tid] = v;
+    }
+}
+
+// One tile of one epilogue thread: row `row` of the tile, columns [hf * HC, hf * HC + HCV) of the accumulator
+// (HCV <= HC valid columns: the rest is padding of an encode_size < 128 and is neither read into the LayerNorm
+// moments nor written anywhere).
+template <bool DROPOUT, int NS, int HC, int HCV>
+__device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *s_vec, float *my_x, const float *qx,
+                                              float (&x)[HC], int q, int hf, int lane, long long vrow0, long long row,
+                                              bool in_range, long long st_idx, float inv_scale, float inv_h)
+{
+    namespace tc = tce;
+    static_assert(HCV % 4 == 0 && HCV >= 4 && HCV <= HC, "valid columns per slice");
+    const float4 *sG = reinterpret_cast<const float4 *>(s_vec + hf * HC);
+    const float4 *sB = reinterpret_cast<const float4 *>(s_vec + tc::H + hf * HC);
+    const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * tc::H + hf * HC);
+    auto xsum = [&](int slot) {
+        float t = 0.0f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) t += qx[(s * 3 + slot) * 32];
+        return t;
+    };
+    // LayerNorm (model.py:55-56), two-pass; x is scale * (c . W^T); slices exchanged via smem
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < HCV; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
+    float part = (s0 + s1) + (s2 + s3);
+    my_x[0] = part;
+    named_bar_sync(1 + q, 32 * NS);
+    const float mean = xsum(0) * inv_h;
+    s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < HCV; c += 4) {
+        const float d0 = x[c] - mean, d1 = x[c + 1] - mean, d2 = x[c + 2] - mean, d3 = x[c + 3] - mean;
+        s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+    }
+    part = (s0 + s1) + (s2 + s3);
+    my_x[32] = part;
+    named_bar_sync(1 + q, 32 * NS);
+    const float var = xsum(1) * inv_h * inv_scale * inv_scale;
+    const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
+    const float shift = -mean * nrm;
+    // tanh (model.py:57), dropout (model.py:60-61), score h.a (model.py:92-93)
+    float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < HCV / 4; ++c4) {
+        const float4 g = sG[c4], b = sB[c4], at = sA[c4];
+        float y0 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 0], nrm, shift), g.x, b.x));
+        float y1 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 1], nrm, shift), g.y, b.y));
+        float y2 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 2], nrm, shift), g.z, b.z));
+        float y3 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 3], nrm, shift), g.w, b.w));
+        if (DROPOUT) {
+            const uint4 bits = dropout_bits(a.seed, row, hf * (HC / 4) + c4);
+            y0 *= dropout_mul(bits.x, a.drop_p, a.drop_scale);
+            y1 *= dropout_mul(bits.y, a.drop_p, a.drop_scale);
+            y2 *= dropout_mul(bits.z, a.drop_p, a.drop_scale);
+            y3 *= dropout_mul(bits.w, a.drop_p, a.drop_scale);
+        }
+        x[4 * c4 + 0] = y0; x[4 * c4 + 1] = y1; x[4 * c4 + 2] = y2; x[4 * c4 + 3] = y3;
+        u0 = fmaf(y0, at.x, u0); u1 = fmaf(y1, at.y, u1);
+        u0 = fmaf(y2, at.z, u0); u1 = fmaf(y3, at.w, u1);
+    }
+#pragma unroll
+    for (int c = HCV; c < (HCV + 31) / 32 * 32; ++c) x[c] = 0.0f;     // padding inside the last 32-column group
+    part = u0 + u1;
+    my_x[64] = part;
+    named_bar_sync(1 + q, 32 * NS);
+    const float u = xsum(2);                                     // same order => same bits in every slice
+    // model.py:93  score*mask + (1-mask)*NINF
+    const float z = (in_range && st_idx > 0) ? u : C2V_NINF;
+    if (hf == 0 && in_range) a.attention[row] = z;
+
+    // per-(warp, bag) online-softmax partial -> slot (vtile + bag); each slice writes its valid columns
+    if (vrow0 < a.N) {
+        const long long vt = vrow0 / tc::VROWS;
+        long long last = vrow0 + tc::VROWS - 1; if (last > a.N - 1) last = a.N - 1;
+        const long long bag_lo = vrow0 / a.L, bag_hi = last / a.L;
+        const long long my_bag = row / a.L;
+        for (long long bag = bag_lo; bag <= bag_hi; ++bag) {
+            const bool in_seg = in_range && my_bag == bag;
+            const float m = warp_max(in_seg ? z : -INFINITY);
+            const float e = in_seg ? __expf(z - m) : 0.0f;
+            const size_t slot = (size_t)(vt + bag);
+            float *pv = a.ws.part_v + slot * a.H + hf * HC;
+#pragma unroll
+            for (int c = 0; c < (HCV + 31) / 32; ++c) {
+                float t[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) t[j] = e * x[c * 32 + j];
+                butterfly_reduce32(t, lane);
+                if (c * 32 + lane < HCV) pv[c * 32 + lane] = t[0];
+            }
+            if (hf == 0) {
+                const float ssum = warp_sum(e);
+                if (lane == 0) { a.ws.part_m[slot] = m; a.ws.part_s[slot] = ssum; }
+            }
+        }
     }
 }
 
@@ -31,7 +131,8 @@ __device__ __forceinline__ void tce_fill_vectors(const EncodeArgs &a, float *s_v
 // NS = column slices per lane quarter (epilogue warps = 4 * NS): warp w handles rows of quarter w & 3 and
 // columns [(w >> 2) * H/NS, ...); LayerNorm moments and the score are summed across the NS warps of a
 // quarter through smem + a named barrier, always in slice order so every warp gets the same bits.
-template <bool DROPOUT, int NS = 2>
+// HV = encode_size (valid accumulator columns, multiple of 4, > (NS-1) * 128/NS); the tile is always 128 wide.
+template <bool DROPOUT, int NS = 2, int HV = 128>
 __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_vec, float *s_xch,
                                                   uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
                                                   int warp, int lane, int my_tiles, long long *status)
@@ -40,18 +141,11 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
         const int q = warp & 3;                 // TMEM lane quarter: rows 32q .. 32q+31 of the tile
         const int hf = warp >> 2;               // column slice: HC*hf .. HC*hf+HC-1
         constexpr int HC = tc::H / NS;          // columns per thread (64 or 32)
+        constexpr int HC_LAST = HV - (NS - 1) * HC;      // valid columns of the last slice
+        static_assert(HC_LAST > 0 && HC_LAST <= HC, "encode_size must reach into the last column slice");
         const float inv_scale = a.ws.prep_hdr[0];
-        const float4 *sG = reinterpret_cast<const float4 *>(s_vec + hf * HC);
-        const float4 *sB = reinterpret_cast<const float4 *>(s_vec + tc::H + hf * HC);
-        const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * tc::H + hf * HC);
         float *my_x = s_xch + ((q * NS + hf) * 3) * 32 + lane;          // [3][32] per (quarter, slice)
         const float *qx = s_xch + (q * NS * 3) * 32 + lane;             // slice s, slot k at qx[(s*3+k)*32]
-        auto xsum = [&](int slot) {
-            float t = 0.0f;
-#pragma unroll
-            for (int s = 0; s < NS; ++s) t += qx[(s * 3 + slot) * 32];
-            return t;
-        };
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
             const int acc = tl & 1;
@@ -73,80 +167,12 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);           // accumulator is free again
             if (a.flags & 16) continue;        // timing experiment: producer side alone (results are wrong)
 
-            // LayerNorm (model.py:55-56), two-pass; x is scale * (c . W^T); halves exchanged via smem
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int c = 0; c < HC; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
-            float part = (s0 + s1) + (s2 + s3);
-            my_x[0] = part;
-            named_bar_sync(1 + q, 32 * NS);
-            const float mean = xsum(0) * (1.0f / tc::H);
-            s0 = s1 = s2 = s3 = 0.f;
-#pragma unroll
-            for (int c = 0; c < HC; c += 4) {
-                const float d0 = x[c] - mean, d1 = x[c + 1] - mean, d2 = x[c + 2] - mean, d3 = x[c + 3] - mean;
-                s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
-            }
-            part = (s0 + s1) + (s2 + s3);
-            my_x[32] = part;
-            named_bar_sync(1 + q, 32 * NS);
-            const float var = xsum(1) * (1.0f / tc::H) * inv_scale * inv_scale;
-            const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
-            const float shift = -mean * nrm;
-            // tanh (model.py:57), dropout (model.py:60-61), score h.a (model.py:92-93)
-            float u0 = 0.f, u1 = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < HC / 4; ++c4) {
-                const float4 g = sG[c4], b = sB[c4], at = sA[c4];
-                float y0 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 0], nrm, shift), g.x, b.x));
-                float y1 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 1], nrm, shift), g.y, b.y));
-                float y2 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 2], nrm, shift), g.z, b.z));
-                float y3 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 3], nrm, shift), g.w, b.w));
-                if (DROPOUT) {
-                    const uint4 bits = dropout_bits(a.seed, row, hf * (HC / 4) + c4);
-                    y0 *= dropout_mul(bits.x, a.drop_p, a.drop_scale);
-                    y1 *= dropout_mul(bits.y, a.drop_p, a.drop_scale);
-                    y2 *= dropout_mul(bits.z, a.drop_p, a.drop_scale);
-                    y3 *= dropout_mul(bits.w, a.drop_p, a.drop_scale);
-                }
-                x[4 * c4 + 0] = y0; x[4 * c4 + 1] = y1; x[4 * c4 + 2] = y2; x[4 * c4 + 3] = y3;
-                u0 = fmaf(y0, at.x, u0); u1 = fmaf(y1, at.y, u1);
-                u0 = fmaf(y2, at.z, u0); u1 = fmaf(y3, at.w, u1);
-            }
-            part = u0 + u1;
-            my_x[64] = part;
-            named_bar_sync(1 + q, 32 * NS);
-            const float u = xsum(2);                                     // same order => same bits in every slice
-            // model.py:93  score*mask + (1-mask)*NINF
-            const float z = (in_range && st_idx > 0) ? u : C2V_NINF;
-            if (hf == 0 && in_range) a.attention[row] = z;
-
-            // per-(warp, bag) online-softmax partial -> slot (vtile + bag); each half writes its 64 columns
-            if (vrow0 < a.N) {
-                const long long vt = vrow0 / tc::VROWS;
-                long long last = vrow0 + tc::VROWS - 1; if (last > a.N - 1) last = a.N - 1;
-                const long long bag_lo = vrow0 / a.L, bag_hi = last / a.L;
-                const long long my_bag = row / a.L;
-                for (long long bag = bag_lo; bag <= bag_hi; ++bag) {
-                    const bool in_seg = in_range && my_bag == bag;
-                    const float m = warp_max(in_seg ? z : -INFINITY);
-                    const float e = in_seg ? __expf(z - m) : 0.0f;
-                    const size_t slot = (size_t)(vt + bag);
-                    float *pv = a.ws.part_v + slot * tc::H + hf * HC;
-#pragma unroll
-                    for (int c = 0; c < HC / 32; ++c) {
-                        float t[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) t[j] = e * x[c * 32 + j];
-                        butterfly_reduce32(t, lane);
-                        pv[c * 32 + lane] = t[0];
-                    }
-                    if (hf == 0) {
-                        const float ssum = warp_sum(e);
-                        if (lane == 0) { a.ws.part_m[slot] = m; a.ws.part_s[slot] = ssum; }
-                    }
-                }
-            }
+            if (HC_LAST == HC || hf < NS - 1)
+                tce_tile_body<DROPOUT, NS, HC, HC>(a, s_vec, my_x, qx, x, q, hf, lane, vrow0, row, in_range, st_idx,
+                                                   inv_scale, 1.0f / (float)HV);
+            else
+                tce_tile_body<DROPOUT, NS, HC, HC_LAST>(a, s_vec, my_x, qx, x, q, hf, lane, vrow0, row, in_range, st_idx,
+                                                        inv_scale, 1.0f / (float)HV);
         }
 }
 

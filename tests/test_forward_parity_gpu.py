@@ -67,6 +67,35 @@ def test_forward_matches_oracle_on_seeded_inputs(algo, B, L):
     assert np.abs(out.cpu().numpy() - ref_out).max() <= EXPECT * 4
 
 
+@pytest.mark.parametrize("E,H", [(100, 100), (128, 100), (100, 128), (64, 128), (36, 100), (4, 100)])
+@pytest.mark.parametrize("B,L", [(3, 200), (37, 50), (130, 31)])
+def test_padded_shapes_on_the_tensor_core_path(E, H, B, L):
+    """K1e pads every sub-vector to 128 k (zero-filled cp.async chunks) and the encode size to 128 columns
+    (masked LayerNorm moments): the reference's default 100/100/100 (main.py:56-58) and other E % 4 == 0,
+    H in {100, 128} shapes against the oracle, through the C ABI with algo = TCGEN05 (no fallback)."""
+    from oracle import oracle
+    rng = np.random.default_rng(E * 1000 + H * 10 + B)
+    T, P, C = 5000, 3000, 77
+    p = random_params(rng, T, P, C, E, E, H)
+    starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
+    starts[1, :] = 0                          # an all-pad bag
+    starts[2, ::3] = 0                        # holes
+    dims = CF.make_dims(T, P, C, E, E, H)
+    assert supports_tcgen05(dict(T=T, P=P, C=C, Et=E, Ep=E, H=H))
+    tp = {k: cuda(v) for k, v in p.items()}
+    params = CF.make_params(tp["terminal_embedding.weight"], tp["path_embedding.weight"], tp["input_linear.weight"],
+                            tp["input_layer_norm.weight"], tp["input_layer_norm.bias"], tp["attention_parameter"],
+                            tp["output_linear.weight"], tp["output_linear.bias"])
+    cv, att = CF.encode_forward(dims, params, cuda(starts), cuda(paths), cuda(ends), algo=_lib.ALGO_TCGEN05, check_indices=True)
+    out = CF.label_logits(dims, params, cv, algo=_lib.ALGO_TCGEN05)
+    ref_out, ref_cv, ref_att = oracle.forward(p, starts, paths, ends, label)
+    assert np.abs(cv.cpu().numpy() - ref_cv).max() <= EXPECT
+    assert np.abs(att.cpu().numpy() - ref_att).max() <= EXPECT
+    assert np.abs(out.cpu().numpy() - ref_out).max() <= EXPECT * 4
+    cvf, attf = CF.encode_forward(dims, params, cuda(starts), cuda(paths), cuda(ends), algo=_lib.ALGO_FFMA)
+    assert np.abs(cvf.cpu().numpy() - cv.cpu().numpy()).max() <= EXPECT
+
+
 @pytest.mark.parametrize("algo", ["ffma", "tcgen05"])
 def test_full_size_properties(algo):
     """BASELINE.json cfg2 batch (1024 x 200, E=H=128): too big for the scalar oracle, so check
@@ -118,14 +147,15 @@ def test_out_of_range_index_is_reported_like_the_reference():
                               check_indices=True)
 
 
+@pytest.mark.parametrize("E,H", [(128, 128), (100, 100)])
 @pytest.mark.parametrize("algo", ["ffma", "tcgen05"])
-def test_training_mode_dropout_matches_oracle_with_same_mask(algo):
+def test_training_mode_dropout_matches_oracle_with_same_mask(algo, E, H):
     """model.py:60-61.  The kernel's mask is a pure function of (seed, row, col); the test rebuilds
     it in numpy (tests/philox_ref.py) and hands it to the oracle, so parity is exact."""
     from oracle import oracle
     from philox_ref import dropout_mask
     rng = np.random.default_rng(3)
-    T, P, C, E, H, B, L = 900, 700, 33, 128, 128, 9, 200
+    T, P, C, B, L = 900, 700, 33, 9, 200
     p = random_params(rng, T, P, C, E, E, H)
     starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
     dims = CF.make_dims(T, P, C, E, E, H)
@@ -203,7 +233,8 @@ def test_host_buffer_api_matches_device_api():
         lib.c2v_session_destroy(sess)
 
 
-@pytest.mark.parametrize("B,C,H", [(1, 5, 128), (37, 77, 128), (130, 1000, 128), (1024, 8192, 128), (64, 300, 64), (9, 50, 100)])
+@pytest.mark.parametrize("B,C,H", [(1, 5, 128), (37, 77, 128), (130, 1000, 128), (1024, 8192, 128), (64, 300, 64), (9, 50, 100),
+                                   (200, 2279, 100), (33, 70, 36), (5, 40, 130)])
 def test_label_logits_tcgen05_vs_ffma_vs_oracle(B, C, H):
     """model.py:83 on the tensor cores (3-pass fp16 split) against the CUDA-core GEMM and the oracle,
     incl. ragged tile edges and weights at 'trained' scale."""
@@ -218,7 +249,7 @@ def test_label_logits_tcgen05_vs_ffma_vs_oracle(B, C, H):
     tol = 3e-6 * max(1.0, float(np.abs(ref).max()))      # fp32 relative: logits reach +-30 here
     out_f = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_FFMA).cpu().numpy()
     assert np.abs(out_f - ref).max() <= tol
-    if H in (64, 128):
+    if H % 4 == 0 and H <= 128:
         out_t = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_TCGEN05).cpu().numpy()
         assert np.abs(out_t - ref).max() <= tol, np.abs(out_t - ref).max()
         out_a = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_AUTO).cpu().numpy()
