@@ -36,6 +36,10 @@ WORKLOADS = {
     # configs[4]: large-vocab stress (gather-bound)
     "cfg5": dict(T=2000000, P=500000, C=8192, Et=128, Ep=128, H=128, B=1024, L=200,
                  desc="large-vocab stress: 2M terminals / 500K paths, embed=128, encode=128, batch=1024"),
+    # configs[2]: top11 corpus sizes (the reference's default embed/encode 100), synthetic uniform indices
+    "cfg3": dict(T=360633, P=342846, C=195299, Et=100, Ep=100, H=100, B=1024, L=200,
+                 desc="top11_dataset sizes: T=360,633 P=342,846 C=195,299, embed=100/100, encode=100, batch=1024 "
+                      "(synthetic uniform indices; the corpus itself is not shipped)"),
     # small variant for quick functional runs
     "tiny": dict(T=5000, P=4000, C=256, Et=128, Ep=128, H=128, B=64, L=200, desc="tiny functional run"),
 }

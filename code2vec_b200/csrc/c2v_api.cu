@@ -1,6 +1,7 @@
 // c2v_api.cu -- the extern "C" surface declared in include/c2v_b200.h.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -9,6 +10,12 @@
 namespace c2v {
 
 long long g_launches = 0;
+bool pdl_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("C2V_NO_PDL"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on == 1;
+}
 static thread_local char g_err[512] = "";
 
 void set_error(const char *fmt, ...)

@@ -37,6 +37,25 @@ extern long long g_launches;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+#ifdef __CUDACC__
+// Programmatic dependent launch: the kernel may start (prologue, block scheduling) while the previous kernel of the
+// stream is still draining; it must execute griddepcontrol.wait (pdl_wait()) before touching anything the previous
+// kernel wrote.  C2V_NO_PDL=1 falls back to a plain launch (A/B timing).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // ---------------------------------------------------------------------------------
 // workspace layout of one encode call (all offsets 256-B aligned)
 // ---------------------------------------------------------------------------------

@@ -157,6 +157,7 @@ int launch_encode_ffma(const EncodeArgs &a, cudaStream_t st)
 __global__ void __launch_bounds__(128)
 encode_finalize_kernel(const EncodeArgs a, const int tile_rows, float *__restrict__ code_vector)
 {
+    pdl_wait();                                   // launched as a programmatic dependent of the encode kernel
     const long long bag = blockIdx.x;
     const int L = a.L, H = a.H;
     const long long r0 = bag * L;
@@ -185,7 +186,7 @@ encode_finalize_kernel(const EncodeArgs a, const int tile_rows, float *__restric
 
 int launch_encode_finalize(const EncodeArgs &a, int B, float *code_vector, cudaStream_t st)
 {
-    encode_finalize_kernel<<<B, 128, 0, st>>>(a, a.ws.tile_rows, code_vector);
+    C2V_CUDA_OK(launch_pdl(encode_finalize_kernel, dim3((unsigned)B), dim3(128), 0, st, a, a.ws.tile_rows, code_vector));
     C2V_LAUNCH_OK("encode_finalize_kernel");
     return C2V_OK;
 }

@@ -53,10 +53,6 @@ static_assert(A_COL0 + A_STAGES * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
 __device__ __forceinline__ void tm_cp_async_cg16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-// src_bytes = 0: nothing is read, the 16 bytes are zero-filled (padding of an embedding size < 128)
-__device__ __forceinline__ void tm_cp_async_cg16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
 __device__ __forceinline__ void tm_cp_async_mbar_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -148,6 +144,10 @@ encode_tm_kernel(const EncodeArgs a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tce_fill_vectors(a, s_vec, tid);
+    if (!FULL_E) {      // padding chunks of the raw stages (k >= embed size) are read by the converters but never written
+        uint4 *z = reinterpret_cast<uint4 *>(smem + tm::SMEM_RAW_OFF);
+        for (int i = tid; i < tm::RAW_STAGES * tm::RAW_BYTES / 16; i += tm::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -272,9 +272,8 @@ encode_tm_kernel(const EncodeArgs a)
                         const uint32_t chunk = (uint32_t)(h * tm::RAW_ROW_BYTES) + qoff[j & 3];   // byte offset in the row
                         if (FULL_E) {
                             if (!(a.flags & 64)) tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o[j] + chunk));
-                        } else {        // chunks at or beyond the embedding size are zero-filled, not read
-                            const bool real = chunk < row_bytes;
-                            tm_cp_async_cg16_zfill(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o[j] + (real ? chunk : 0u)), real ? 16u : 0u);
+                        } else if (chunk < row_bytes) {     // chunk positions at or beyond the embedding size are never
+                            tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o[j] + chunk));   // written: zero since start
                         }
                     }
                     tm_cp_async_mbar_arrive_noinc(bar_rfull + 8 * st);
@@ -311,6 +310,7 @@ encode_tm_kernel(const EncodeArgs a)
                         const uint32_t ta = ta0 + (uint32_t)(as * tm::A_STAGE_COLS);
 #pragma unroll
                         for (int k = 0; k < tm::KB / 16; ++k) {
+                            if (!FULL_E && (kb & 1) * tm::KB + k * 16 >= a.Et) break;       // k-steps of pure padding
                             const uint32_t a_hi = ta + k * 8, a_lo = ta + tm::KB / 2 + k * 8;
                             const uint64_t w_hi = w_hi0 + (uint64_t)(k * 2);                  // + 32 B
                             const uint64_t w_lo = w_hi + (uint64_t)(tm::TILE_BYTES >> 4);

@@ -178,6 +178,10 @@ loss_argmax_kernel(const float *__restrict__ out, const long long *__restrict__ 
     mx = s_val[0]; am = s_idx[0];
     for (int w = 1; w < 8; ++w)
         if (s_val[w] > mx || (s_val[w] == mx && s_idx[w] < am)) { mx = s_val[w]; am = s_idx[w]; }
+    if (!(loss && label) && !(d_out && label)) {          // arg-max only: no second pass over the logits
+        if (tid == 0) { if (argmax) argmax[b] = am; if (maxval) maxval[b] = mx; }
+        return;
+    }
     float s = 0.0f;
     for (long long c = tid; c < C; c += 256) s += __expf(r[c] - mx);
     s = warp_sum(s);

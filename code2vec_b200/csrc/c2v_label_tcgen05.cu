@@ -11,6 +11,8 @@
 // stores with the bias added.  Output-write bound (B*C*4 bytes).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "c2v_common.cuh"
 
 namespace c2v {
@@ -18,8 +20,6 @@ namespace c2v {
 namespace lt {
 constexpr int TM = 128, TN = 128, KB = 64;
 constexpr int TILE_BYTES = 128 * KB * 2;          // 16 KB
-constexpr int MAX_NKB = 2;                        // encode_size 64 or 128
-constexpr int STAGE_LD = 132;                     // padded fp32 row of the output staging tile
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }  // namespace lt
 
@@ -41,8 +41,10 @@ __global__ void absmax_kernel(const float *__restrict__ x, long long n, unsigned
 // scale_bits == nullptr: no scaling.  Rows >= R are zero-filled.  hdr[0] = 1/scale, hdr[1] = scale.
 __global__ void split_rows_kernel(const float *__restrict__ X, long long R, int K, int nkb,
                                   const unsigned *__restrict__ scale_bits, uint8_t *__restrict__ img,
-                                  float *__restrict__ hdr)
+                                  float *__restrict__ hdr, unsigned long long *__restrict__ zero_u64, int n_zero)
 {
+    pdl_wait();                                   // (no-op unless launched as a programmatic dependent)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero_u64[i] = 0ull;
     float scale = 1.0f;
     if (scale_bits) {
         const float mx = __uint_as_float(*scale_bits);
@@ -84,185 +86,304 @@ __device__ __forceinline__ void lt_mbar_wait(uint32_t bar, uint32_t parity) {
         if (!ok && spins > (1u << 26)) __trap();
     }
 }
+__device__ __forceinline__ bool lt_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// monotone float -> uint32 map, so that (key(value) << 32 | ~column) ordered as uint64 picks the largest value and,
+// among equal values, the smallest column: torch.max(dim=1) semantics (main.py:285)
+__device__ __forceinline__ uint32_t lt_orderable(float v) {
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float lt_from_orderable(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
 
-// Persistent label GEMM.  Grid = (G, n_mt): CTA (g, mt) keeps the cv image of m-tile mt resident and walks
-// the n-tiles g, g+G, ...; W_out tiles are double buffered in smem, accumulators in TMEM, so the bulk copy of
-// tile i+1, the MMAs of tile i and the epilogue (TMEM -> registers -> +bias -> row stores, running argmax) of
-// tile i-1 overlap.  Warps 0-3: epilogue (one output row per thread); warp 4: loads + TMEM alloc; warp 5: MMA.
-__global__ void __launch_bounds__(192, 1)
-label_gemm_tcgen05_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict__ imgB,
-                          const float *__restrict__ bias, const float *__restrict__ hdr,
-                          float *__restrict__ out, int M, long long N, int nkb, int n_nt)
+// Tile order: groups of NT_GROUP consecutive n-tiles; inside a group m-tile major, n-tile minor.  A CTA's consecutive
+// tiles then write adjacent 512-B pieces of the same 128 output rows within a few microseconds (L2 merges them into
+// long DRAM bursts: with n-tile-major order the label GEMM wrote at 2.2 TB/s, with contiguous 4 KB runs at 4.2 TB/s),
+// and the W_out tiles of a group (NT_GROUP x 64 KB) are re-read from L2 by the n_mt m-tiles.
+struct LtTile { long long nt; int mt; };
+__device__ __forceinline__ LtTile lt_tile(long long t, int n_mt, long long n_nt, int group) {
+    const long long per_group = (long long)group * n_mt;
+    const long long g = t / per_group;
+    const long long rem = t - g * per_group;
+    long long gs = n_nt - g * group; if (gs > group) gs = group;           // the last group may be narrower
+    LtTile r;
+    r.mt = (int)(rem / gs);
+    r.nt = g * group + (rem - (long long)r.mt * gs);
+    return r;
+}
+
+namespace lt2 {
+constexpr int NT_GROUP = 8;
+constexpr int N_EPI_WARPS = 16;                 // warp w: TMEM lane quarter w & 3, column quarter w >> 2 (32 columns)
+constexpr int LOAD_WARP = 16, MMA_WARP = 17;
+constexpr int THREADS = 18 * 32;
+constexpr int OP_STAGES = 2, ACC_STAGES = 4;
+constexpr int STAGE_BYTES = 4 * lt::TILE_BYTES;              // one k-block: {A_hi, A_lo | B_hi, B_lo}, 64 KB
+constexpr int STG_LD = 36;                                   // padded fp32 row of a warp's [32 x 32] staging tile
+constexpr int STG_BYTES = N_EPI_WARPS * 32 * STG_LD * 4;     // 72 KB
+constexpr int MAX_MT = 16;                                   // running arg-max table: 16 m-tiles x 128 rows x u64
+constexpr int TAB_BYTES = MAX_MT * 128 * 8;
+constexpr int SMEM_STG_OFF = OP_STAGES * STAGE_BYTES;
+constexpr int SMEM_TAB_OFF = SMEM_STG_OFF + STG_BYTES;
+constexpr int SMEM_BIAS_OFF = SMEM_TAB_OFF + TAB_BYTES;      // [16 warps][32] bias of the current tile
+constexpr int SMEM_BAR_OFF = SMEM_BIAS_OFF + N_EPI_WARPS * 32 * 4;
+constexpr int SMEM_BYTES = SMEM_BAR_OFF + 128 + 1024;
+}  // namespace lt2
+
+// K2 v2: persistent label GEMM with the arg-max folded in.  The 128 x 128 output tiles are numbered n-tile major /
+// m-tile minor and cut into one contiguous range per CTA (all SMs busy for any B, C; a CTA's consecutive tiles share
+// their W_out tile, which is therefore read from HBM once and re-read from L2).  Warp 16 streams {cv tile, W_out tile}
+// k-block images through a 2-stage ring (one 32 KB cp.async.bulk each), warp 17 issues 12 tcgen05.mma per k-block into one of
+// four TMEM accumulators, 16 epilogue warps (32 rows x 32 columns each) do TMEM -> registers -> *1/scale + bias ->
+// running arg-max (smem table, 64-bit atomicMax) -> padded smem tile -> row-contiguous 128-B stores.
+// Bound: the logits write (B*C*4 bytes); the arg-max costs no extra pass over them.
+__global__ void __launch_bounds__(lt2::THREADS, 1)
+label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict__ imgB,
+                     const float *__restrict__ bias, const float *__restrict__ hdr, float *__restrict__ out,
+                     int M, long long N, int nkb, int n_mt, long long n_nt, long long n_tiles,
+                     unsigned long long *__restrict__ keys, unsigned *__restrict__ ticket,
+                     long long *__restrict__ argmax, float *__restrict__ maxval, int dbg)
 {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = lt_smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char *smem = smem_raw + (base - raw);
-    const int op_bytes = nkb * 2 * lt::TILE_BYTES;                    // one operand tile image: 32 KB per k-block
-    const uint32_t sA = base, sB0 = base + op_bytes;
-    constexpr int STAGE_BYTES = 4 * 32 * lt::STAGE_LD * 4;           // per-warp [32 rows][132] fp32 output staging
-    float *stage_all = reinterpret_cast<float *>(smem + 2 * op_bytes);
-    const int bar_off = 2 * op_bytes + STAGE_BYTES;
-    const uint32_t bars = base + bar_off;                             // a_full @0, b_full @8, b_empty @24,
-    const uint32_t bar_afull = bars, bar_bfull = bars + 8, bar_bempty = bars + 24,   // t_full[2] @40, t_empty[2] @56
-                   bar_tfull = bars + 40, bar_tempty = bars + 56;
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + bar_off + 72);
+    float *stage_all = reinterpret_cast<float *>(smem + lt2::SMEM_STG_OFF);
+    unsigned long long *tab = reinterpret_cast<unsigned long long *>(smem + lt2::SMEM_TAB_OFF);
+    const uint32_t bars = base + lt2::SMEM_BAR_OFF;
+    // op_full[2] @0, op_empty[2] @16, t_full[4] @32, t_empty[4] @64, tmem ptr @96
+    const uint32_t bar_ofull = bars, bar_oempty = bars + 16, bar_tfull = bars + 32, bar_tempty = bars + 64;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + lt2::SMEM_BAR_OFF + 96);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = blockIdx.y, g = blockIdx.x, G = gridDim.x;
-    const int my_tiles = g < n_nt ? (n_nt - g + G - 1) / G : 0;
+    const long long t_lo = n_tiles * blockIdx.x / gridDim.x, t_hi = n_tiles * (blockIdx.x + 1) / gridDim.x;
+    const int my_tiles = (int)(t_hi - t_lo);
+    const bool want_arg = keys != nullptr;
 
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_afull));
-        for (int s = 0; s < 2; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_bfull + 8 * s));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_bempty + 8 * s));
+        for (int s = 0; s < lt2::OP_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_ofull + 8 * s));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_oempty + 8 * s));
+        }
+        for (int s = 0; s < lt2::ACC_STAGES; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_tfull + 8 * s));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(bar_tempty + 8 * s));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_tempty + 8 * s), "r"((uint32_t)lt2::N_EPI_WARPS));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lt_smem_u32(tmem_ptr_smem)), "r"(256u) : "memory");
+    if (want_arg)
+        for (int i = tid; i < lt2::MAX_MT * 128; i += lt2::THREADS) tab[i] = 0ull;
+    if (warp == lt2::MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(lt_smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_ptr_smem;
+    pdl_wait();                                   // everything above overlapped the tail of the cv-image kernel
 
-    if (warp == 4) {
-        if (lane == 0 && my_tiles > 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_afull), "r"((uint32_t)op_bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(sA), "l"(imgA + (size_t)mt * op_bytes), "r"((uint32_t)op_bytes), "r"(bar_afull) : "memory");
-            for (int i = 0; i < my_tiles; ++i) {        // single W_out buffer: refilled as soon as tile i-1's MMAs retire,
-                const long long nt = g + (long long)i * G;   // i.e. while the epilogue of tile i-1 is still storing
-                lt_mbar_wait(bar_bempty, ((uint32_t)i & 1u) ^ 1u);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_bfull), "r"((uint32_t)op_bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(sB0), "l"(imgB + (size_t)nt * op_bytes), "r"((uint32_t)op_bytes), "r"(bar_bfull) : "memory");
+    const int kb_bytes = 2 * lt::TILE_BYTES;                          // {hi, lo} of one k-block of one operand
+    if (warp == lt2::LOAD_WARP) {
+        if (lane == 0) {
+            int it = 0;
+            for (int i = 0; i < my_tiles; ++i) {
+                const LtTile tt = lt_tile(t_lo + i, n_mt, n_nt, lt2::NT_GROUP);
+                const long long nt = tt.nt; const int mt = tt.mt;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int st = it & 1;
+                    const uint32_t dst = base + st * lt2::STAGE_BYTES;
+                    lt_mbar_wait(bar_oempty + 8 * st, ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_ofull + 8 * st), "r"((uint32_t)(2 * kb_bytes)) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst), "l"(imgA + ((size_t)mt * nkb + kb) * kb_bytes), "r"((uint32_t)kb_bytes), "r"(bar_ofull + 8 * st) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst + kb_bytes), "l"(imgB + ((size_t)nt * nkb + kb) * kb_bytes), "r"((uint32_t)kb_bytes), "r"(bar_ofull + 8 * st) : "memory");
+                }
             }
         }
         __syncwarp();
-    } else if (warp == 5) {
-        if (lane == 0 && my_tiles > 0) {
-            lt_mbar_wait(bar_afull, 0);
-            for (int i = 0; i < my_tiles; ++i) {
-                const int st = i & 1;
-                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-                lt_mbar_wait(bar_tempty + 8 * st, ph ^ 1u);
-                lt_mbar_wait(bar_bfull, (uint32_t)i & 1u);
+    } else if (warp == lt2::MMA_WARP) {
+        // converged warp, one elected lane issues (a divergent `if (lane == 0)` makes ptxas wrap every UTCHMMA in an
+        // ELECT / BRA.U.ANY loop and rebuild the descriptors through R2UR: the issuer becomes the slowest stage)
+        auto desc = [](uint32_t a) {
+            return (uint64_t)((a & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+        };
+        int it = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int acc = i & (lt2::ACC_STAGES - 1);
+            lt_mbar_wait(bar_tempty + 8 * acc, ((uint32_t)(i / lt2::ACC_STAGES) & 1u) ^ 1u);
+            const uint32_t d_tmem = tmem + (uint32_t)(acc * lt::TN);
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int st = it & 1;
+                lt_mbar_wait(bar_ofull + 8 * st, (uint32_t)(it >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem + (uint32_t)(st * lt::TN);
-                for (int kb = 0; kb < nkb; ++kb) {
+                if (lt_elect_one()) {
+                    const uint64_t a0 = desc(base + st * lt2::STAGE_BYTES);
+                    const uint64_t b0 = a0 + (uint64_t)(kb_bytes >> 4);
 #pragma unroll
                     for (int k = 0; k < lt::KB / 16; ++k) {
-                        auto desc = [](uint32_t a) {
-                            return (uint64_t)((a & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-                        };
-                        const uint32_t a0 = sA + kb * 2 * lt::TILE_BYTES + k * 32;
-                        const uint32_t b0 = sB0 + kb * 2 * lt::TILE_BYTES + k * 32;
-                        const uint64_t a_hi = desc(a0), a_lo = desc(a0 + lt::TILE_BYTES), b_hi = desc(b0), b_lo = desc(b0 + lt::TILE_BYTES);
-                        auto mma = [&](uint64_t ad, uint64_t bd, uint32_t acc) {
+                        const uint64_t a_hi = a0 + (uint64_t)(k * 2), a_lo = a_hi + (lt::TILE_BYTES >> 4);
+                        const uint64_t b_hi = b0 + (uint64_t)(k * 2), b_lo = b_hi + (lt::TILE_BYTES >> 4);
+                        auto mma = [&](uint64_t ad, uint64_t bd, uint32_t accum) {
                             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                                         ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(lt::IDESC), "r"(acc) : "memory");
+                                         ::"r"(d_tmem), "l"(ad), "l"(bd), "r"(lt::IDESC), "r"(accum) : "memory");
                         };
                         mma(a_hi, b_hi, (kb | k) != 0 ? 1u : 0u);
                         mma(a_lo, b_hi, 1u);
                         mma(a_hi, b_lo, 1u);
                     }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_oempty + 8 * st) : "memory");
+                    if (kb == nkb - 1)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull + 8 * acc) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_bempty) : "memory");
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_tfull + 8 * st) : "memory");
+                __syncwarp();
             }
         }
-        __syncwarp();
     } else {
-        // ---- epilogue: thread = output row of the m-tile; rows leave through a per-warp padded smem tile
-        //      so that every global store instruction writes one full 512-B row segment
+        // ---- epilogue: thread = output row (TMEM lane) x 32 columns.  Bounds and addresses are hoisted out of the
+        //      per-element code (the first version spent 1100 instructions per warp and tile, 60 % issue-bound).
+        const int q = warp & 3, cq = warp >> 2;
         const float inv_scale = hdr[0];
         const bool vec_ok = (N % 4 == 0);
-        float *stg = stage_all + warp * 32 * lt::STAGE_LD;
+        float *stg = stage_all + warp * 32 * lt2::STG_LD;
+        float *sbias = reinterpret_cast<float *>(smem + lt2::SMEM_BIAS_OFF) + warp * 32;
         for (int i = 0; i < my_tiles; ++i) {
-            const int st = i & 1;
-            const long long nt = g + (long long)i * G;
-            lt_mbar_wait(bar_tfull + 8 * st, (uint32_t)(i >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(st * lt::TN);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                             : "r"(taddr + c * 32));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c == 3) {   // all 128 columns have left TMEM: the accumulator can be reused
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8 * st) : "memory");
-                }
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4 *>(stg + lane * lt::STAGE_LD + c * 32 + j) =
-                        make_float4(__uint_as_float(r[j]) * inv_scale, __uint_as_float(r[j + 1]) * inv_scale,
-                                    __uint_as_float(r[j + 2]) * inv_scale, __uint_as_float(r[j + 3]) * inv_scale);
-            }
+            const LtTile tt = lt_tile(t_lo + i, n_mt, n_nt, lt2::NT_GROUP);
+            const long long nt = tt.nt; const int mt = tt.mt;
+            const int acc = i & (lt2::ACC_STAGES - 1);
+            const long long col0 = nt * lt::TN + cq * 32;              // first column of this warp's block
+            const long long row0 = (long long)mt * lt::TM + q * 32;    // first row
+            const int n_cols = (int)(N - col0 < 32 ? N - col0 : 32);   // valid columns / rows of the block (may be <= 0)
+            const int n_rows = (int)(M - row0 < 32 ? M - row0 : 32);
+            // bias of this warp's 32 columns: one element per lane -> smem -> broadcast float4 reads
+            sbias[lane] = (bias && lane < n_cols) ? __ldg(bias + col0 + lane) : 0.0f;
             __syncwarp();
-            // coalesced copy-out (+bias, model.py:83): each store instruction writes one full 512-B row segment
-            const long long col = nt * lt::TN + lane * 4;
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias) {
-                if (col + 3 < N) bv = __ldg(reinterpret_cast<const float4 *>(bias + col));
-                else { if (col < N) bv.x = bias[col]; if (col + 1 < N) bv.y = bias[col + 1]; if (col + 2 < N) bv.z = bias[col + 2]; }
+            lt_mbar_wait(bar_tfull + 8 * acc, (uint32_t)(i / lt2::ACC_STAGES) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * lt::TN + cq * 32);
+            uint32_t r[32];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tempty + 8 * acc) : "memory");
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {                                                       // model.py:83
+                const float4 b4 = *reinterpret_cast<const float4 *>(sbias + j);
+                v[j] = fmaf(__uint_as_float(r[j]), inv_scale, b4.x); v[j + 1] = fmaf(__uint_as_float(r[j + 1]), inv_scale, b4.y);
+                v[j + 2] = fmaf(__uint_as_float(r[j + 2]), inv_scale, b4.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), inv_scale, b4.w);
             }
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-                const int orow_i = mt * lt::TM + warp * 32 + rr;
-                if (orow_i >= M) break;
-                float4 v = *reinterpret_cast<const float4 *>(stg + rr * lt::STAGE_LD + lane * 4);
-                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                float *o = out + (size_t)orow_i * N + col;
-                if (vec_ok && col + 3 < N) *reinterpret_cast<float4 *>(o) = v;
-                else {
-                    if (col < N) o[0] = v.x;
-                    if (col + 1 < N) o[1] = v.y;
-                    if (col + 2 < N) o[2] = v.z;
-                    if (col + 3 < N) o[3] = v.w;
+            if (want_arg && lane < n_rows && n_cols > 0 && !(dbg & 2)) {
+                float m = -INFINITY;
+                if (n_cols == 32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m = fmaxf(m, j < n_cols ? v[j] : -INFINITY);
+                }
+                unsigned long long *slot = tab + mt * 128 + q * 32 + lane;
+                const uint32_t mk = lt_orderable(m);
+                if (mk >= (uint32_t)(*reinterpret_cast<volatile unsigned long long *>(slot) >> 32)) {
+                    int jm = 31;
+#pragma unroll
+                    for (int j = 31; j >= 0; --j) jm = (v[j] == m && j < n_cols) ? j : jm;        // first maximum
+                    atomicMax(slot, ((unsigned long long)mk << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(col0 + jm)));
                 }
             }
-            __syncwarp();                         // staging tile is rewritten by the next n-tile
+            // registers -> padded smem tile (thread = row), then row-contiguous stores
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4 *>(stg + lane * lt2::STG_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+            if (dbg & 4) {          // timing experiment: same bytes, but every warp block as one contiguous 4 KB run
+                float *gp = out + ((size_t)(t_lo + i) * 16 + warp) * 1024 + lane * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                    *reinterpret_cast<float4 *>(gp + it * 128) = *reinterpret_cast<const float4 *>(stg + (it * 4 + (lane >> 3)) * lt2::STG_LD + (lane & 7) * 4);
+            } else if (n_rows > 0 && n_cols > 0 && !(dbg & 1)) {
+                if (vec_ok && n_cols == 32) {
+                    const int rr0 = lane >> 3, c4 = (lane & 7) * 4;          // 4 rows x 128 B per store instruction
+                    float *gp = out + (size_t)(row0 + rr0) * N + col0 + c4;
+                    const float *sp = stg + rr0 * lt2::STG_LD + c4;
+                    const size_t gstep = (size_t)4 * N;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        if (it * 4 + rr0 < n_rows) *reinterpret_cast<float4 *>(gp) = *reinterpret_cast<const float4 *>(sp + it * 4 * lt2::STG_LD);
+                        gp += gstep;
+                    }
+                } else if (lane < n_cols) {                                  // one <= 128-B row segment per store instruction
+                    float *gp = out + (size_t)row0 * N + col0 + lane;
+                    const float *sp = stg + lane;
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) {
+                        if (rr < n_rows) *gp = sp[rr * lt2::STG_LD];
+                        gp += N;
+                    }
+                }
+            }
+            __syncwarp();                         // staging tile is rewritten by the next tile
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == lt2::MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+    if (want_arg) {
+        // flush this CTA's table, then the last CTA to arrive decodes keys -> (argmax, maxval)
+        __shared__ unsigned s_last;
+        for (int i = tid; i < n_mt * 128; i += lt2::THREADS) {
+            const unsigned long long k = tab[i];
+            if (k != 0ull && i < M) atomicMax(keys + i, k);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int b = tid; b < M; b += lt2::THREADS) {
+                const unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(keys + b);
+                if (argmax) argmax[b] = (long long)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull));
+                if (maxval) maxval[b] = lt_from_orderable((uint32_t)(k >> 32));
+            }
+        }
     }
 }
 
 // K (= encode_size) is zero-padded to a multiple of 64 inside the operand images
 bool label_tcgen05_shape_ok(const c2v_dims *d) { return d->encode >= 4 && d->encode <= 128 && (d->encode & 3) == 0; }
 
+static size_t lt_keys_bytes(int B) { return ((size_t)B * 8 + 1023) / 1024 * 1024; }
+
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B)
 {
     const size_t nkb = (size_t)(d->encode + 63) / 64;
     const size_t mt = (size_t)(B + 127) / 128, nt = (size_t)(d->label_count + 127) / 128;
-    return 1024 + (mt + nt) * nkb * 2 * lt::TILE_BYTES;
+    return 1024 + lt_keys_bytes(B) + (mt + nt) * nkb * 2 * lt::TILE_BYTES;
 }
 
 int launch_loss_argmax(const float *out, const long long *label, int B, long long C, float *loss,
                        long long *argmax, float *maxval, float *d_out, cudaStream_t st);
 
-// argmax / maxval (torch.max(dim=1), main.py:285): a second pass over the logits, which are still in L2
-// (B*C*4 = 33.5 MB at cfg2).  Folding it into the GEMM epilogue was measured slower (shuffle argmax 52 us,
-// register argmax 44 us, vs 20.6 + 10.3 us for GEMM + this pass; scripts/time_label.py).
+// argmax / maxval (torch.max(dim=1), main.py:285) are folded into the GEMM epilogue (label_gemm_v2_kernel) for up to
+// 16 m-tiles (B <= 2048); beyond that they are a second pass over the logits.
 int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float *Wout, const float *bias,
                          float *out, long long *argmax, float *maxval, void *ws, size_t ws_bytes, bool reuse_prep,
                          cudaStream_t st)
@@ -280,10 +401,13 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
     uint8_t *p = static_cast<uint8_t *>(ws);
     float *hdr = reinterpret_cast<float *>(p);
     unsigned *mxbits = reinterpret_cast<unsigned *>(p + 256);
+    unsigned *ticket = reinterpret_cast<unsigned *>(p + 512);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(p + 1024);
     const size_t mt = (size_t)(B + 127) / 128, nt = (size_t)((C + 127) / 128);
-    // W_out image first (reusable across calls while the weights are unchanged), cv image, argmax keys
-    uint8_t *imgB = p + 1024, *imgA = imgB + nt * nkb * 2 * lt::TILE_BYTES;
+    // W_out image first (reusable across calls while the weights are unchanged), then the cv image
+    uint8_t *imgB = p + 1024 + lt_keys_bytes(B), *imgA = imgB + nt * nkb * 2 * lt::TILE_BYTES;
     const bool want_arg = argmax || maxval;
+    const bool fused_arg = want_arg && mt <= (size_t)lt2::MAX_MT;
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -292,22 +416,25 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
         C2V_CUDA_OK(cudaMemsetAsync(mxbits, 0, 4, st));
         absmax_kernel<<<sms * 4, 256, 0, st>>>(Wout, C * H, mxbits);
         C2V_LAUNCH_OK("absmax_kernel");
-        split_rows_kernel<<<sms * 8, 256, 0, st>>>(Wout, C, H, nkb, mxbits, imgB, hdr);
+        split_rows_kernel<<<sms * 8, 256, 0, st>>>(Wout, C, H, nkb, mxbits, imgB, hdr, nullptr, 0);
         C2V_LAUNCH_OK("split_rows_kernel");
     }
-    split_rows_kernel<<<(unsigned)((mt * 128 * nkb * 16 + 255) / 256), 256, 0, st>>>(cv, B, H, nkb, nullptr, imgA, hdr);
-    C2V_LAUNCH_OK("split_rows_kernel");
+    // cv image (+ zeroes the ticket and the arg-max keys, which sit contiguously at p + 512)
+    C2V_CUDA_OK(launch_pdl(split_rows_kernel, dim3((unsigned)((mt * 128 * nkb * 16 + 255) / 256)), dim3(256), 0, st, cv,
+                           (long long)B, H, nkb, (const unsigned *)nullptr, imgA, hdr,
+                           reinterpret_cast<unsigned long long *>(p + 512), fused_arg ? 64 + B : 0));
+    C2V_COUNT_LAUNCH();
 
-    const int op_bytes = nkb * 2 * lt::TILE_BYTES;
-    const int smem_bytes = 2 * op_bytes + 4 * 32 * lt::STAGE_LD * 4 + 128 + 1024;
-    C2V_CUDA_OK(cudaFuncSetAttribute(label_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    int G = sms / (int)mt;
-    if (G < 1) G = 1;
-    if (G > (int)nt) G = (int)nt;
-    dim3 grid((unsigned)G, (unsigned)mt);
-    label_gemm_tcgen05_kernel<<<grid, 192, smem_bytes, st>>>(imgA, imgB, bias, hdr, out, B, C, nkb, (int)nt);
-    C2V_LAUNCH_OK("label_gemm_tcgen05_kernel");
-    if (want_arg) return launch_loss_argmax(out, nullptr, B, C, nullptr, argmax, maxval, nullptr, st);
+    C2V_CUDA_OK(cudaFuncSetAttribute(label_gemm_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt2::SMEM_BYTES));
+    const long long n_tiles = (long long)mt * (long long)nt;
+    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    C2V_CUDA_OK(launch_pdl(label_gemm_v2_kernel, dim3((unsigned)grid), dim3(lt2::THREADS), (size_t)lt2::SMEM_BYTES, st,
+                           (const uint8_t *)imgA, (const uint8_t *)imgB, bias, (const float *)hdr, out, B, C, nkb, (int)mt,
+                           (long long)nt, n_tiles, fused_arg ? keys : (unsigned long long *)nullptr, ticket,
+                           fused_arg ? argmax : (long long *)nullptr, fused_arg ? maxval : (float *)nullptr,
+                           getenv("C2V_K2_FLAGS") ? atoi(getenv("C2V_K2_FLAGS")) : 0));
+    C2V_LAUNCH_OK("label_gemm_v2_kernel");
+    if (want_arg && !fused_arg) return launch_loss_argmax(out, nullptr, B, C, nullptr, argmax, maxval, nullptr, st);
     return C2V_OK;
 }
 

@@ -259,7 +259,7 @@ def test_label_logits_tcgen05_vs_ffma_vs_oracle(B, C, H):
             CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_TCGEN05)
 
 
-@pytest.mark.parametrize("B,C", [(1, 5), (37, 77), (1024, 8192), (130, 1000)])
+@pytest.mark.parametrize("B,C", [(1, 5), (37, 77), (1024, 8192), (130, 1000), (300, 1001), (2100, 300), (1024, 19531)])
 def test_fused_label_argmax_matches_torch_max(B, C):
     """main.py:285 folded into the label GEMM epilogue: same logits, first maximum wins, ties included."""
     rng = np.random.default_rng(B + C)
