@@ -162,6 +162,46 @@ encode_finalize_kernel(const EncodeArgs a, const int tile_rows, float *__restric
     const int L = a.L, H = a.H;
     const long long r0 = bag * L;
     const int t0 = (int)(r0 / tile_rows), t1 = (int)((r0 + L - 1) / tile_rows);
+    const int np = t1 - t0 + 1;
+    const size_t slot0 = (size_t)t0 + bag;
+    constexpr int NP = 8;                         // partials per bag on the fast path (L = 200, 32-row slices: 7 or 8)
+    if (np <= NP && H <= 128) {
+        // every load is issued before anything is consumed: one L2 round trip instead of a chain of three
+        float pm[NP], ps[NP], pv[NP], z[2];
+        const int h = threadIdx.x;
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+            const bool on = t < np;
+            pm[t] = on ? a.ws.part_m[slot0 + t] : C2V_NINF;
+            ps[t] = on ? a.ws.part_s[slot0 + t] : 0.0f;
+            pv[t] = (on && h < H) ? a.ws.part_v[(slot0 + t) * H + h] : 0.0f;
+        }
+        const bool two = L <= 2 * 128;
+        if (two) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) z[k] = (h + k * 128 < L) ? a.attention[r0 + h + k * 128] : 0.0f;
+        }
+        float M = C2V_NINF;
+#pragma unroll
+        for (int t = 0; t < NP; ++t) M = fmaxf(M, pm[t]);
+        float S = 0.0f, v = 0.0f;
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+            const float w = t < np ? __expf(pm[t] - M) : 0.0f;
+            S = fmaf(ps[t], w, S);
+            v = fmaf(pv[t], w, v);
+        }
+        const float inv = 1.0f / S;
+        if (h < H) code_vector[bag * H + h] = v * inv;
+        if (two) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (h + k * 128 < L) a.attention[r0 + h + k * 128] = __expf(z[k] - M) * inv;
+        } else {
+            for (int j = h; j < L; j += 128) a.attention[r0 + j] = __expf(a.attention[r0 + j] - M) * inv;
+        }
+        return;
+    }
     float M = C2V_NINF;
     for (int t = t0; t <= t1; ++t) M = fmaxf(M, a.ws.part_m[(size_t)t + bag]);
     float S = 0.0f;
