@@ -45,6 +45,8 @@ size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B);
 // ---- profiling hook (c2v_profile_enable / c2v_profile_read) ----------------------------
 static const int kProfRing = 4096;
 static bool g_prof_on = false;
+static int g_prof_stride = 1;          // time every n-th encode launch (events between launches defeat
+static long long g_prof_calls = 0;     // programmatic dependent launch, so a bench samples instead)
 static cudaEvent_t g_prof_ev[kProfRing][2];
 static bool g_prof_made = false;
 static int g_prof_pending = 0;
@@ -205,7 +207,10 @@ int c2v_encode_forward(const c2v_dims *d, const c2v_params *p, const int64_t *st
     a.n_tiles = (int)((a.N + cta_rows - 1) / cta_rows);
     a.ws = ws;
 
-    C2V_CUDA_OK(cudaMemsetAsync(ws.status, 0, 256, st));
+    // status[0] accumulates out-of-range indices during the encode kernel; the finalize kernel publishes it to
+    // status[3] and clears it for the next call, so a steady-state call (REUSE_PREP) needs no memset and the encode
+    // kernel can be launched as a programmatic dependent of whatever ran before it on the stream.
+    if (!reuse_prep) C2V_CUDA_OK(cudaMemsetAsync(ws.status, 0, 256, st));
 #ifdef TM_INSTRUMENT
     C2V_CUDA_OK(cudaMemsetAsync(ws.status + 16, 0x7f, 8, st));   // min-reduced slots of the instrumented build
     C2V_CUDA_OK(cudaMemsetAsync(ws.status + 20, 0x7f, 8, st));
@@ -216,7 +221,7 @@ int c2v_encode_forward(const c2v_dims *d, const c2v_params *p, const int64_t *st
                     : launch_transpose_w(p->input_linear, ws.w_t, a.H, a.D, (a.H + 3) / 4 * 4, st);
     if (rc != C2V_OK) return rc;
     int slot = -1;
-    if (g_prof_on) {
+    if (g_prof_on && (g_prof_calls++ % g_prof_stride) == 0) {
         if (g_prof_pending == kProfRing) { rc = prof_drain(); if (rc != C2V_OK) return rc; }
         slot = g_prof_pending;
         C2V_CUDA_OK(cudaEventRecord(g_prof_ev[slot][0], st));
@@ -238,6 +243,8 @@ int c2v_profile_enable(int32_t on)
         g_prof_made = true;
     }
     g_prof_on = on != 0;
+    g_prof_stride = on > 1 ? on : 1;
+    g_prof_calls = 0;
     g_prof_pending = 0; g_prof_ms = 0.0; g_prof_count = 0;
     return C2V_OK;
 }
@@ -256,7 +263,7 @@ int64_t c2v_workspace_status(void *workspace, void *stream)
     if (!workspace) { set_error("workspace is NULL"); return C2V_EINVAL; }
     long long v = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    C2V_CUDA_OK(cudaMemcpyAsync(&v, workspace, sizeof(v), cudaMemcpyDeviceToHost, st));
+    C2V_CUDA_OK(cudaMemcpyAsync(&v, static_cast<const char *>(workspace) + 24, sizeof(v), cudaMemcpyDeviceToHost, st));
     C2V_CUDA_OK(cudaStreamSynchronize(st));
     return v;
 }

@@ -159,6 +159,10 @@ encode_finalize_kernel(const EncodeArgs a, const int tile_rows, float *__restric
 {
     pdl_wait();                                   // launched as a programmatic dependent of the encode kernel
     const long long bag = blockIdx.x;
+    if (bag == 0 && threadIdx.x == 0) {           // publish + clear the out-of-range counter (c2v_api.cu)
+        a.ws.status[3] = a.ws.status[0];
+        a.ws.status[0] = 0;
+    }
     const int L = a.L, H = a.H;
     const long long r0 = bag * L;
     const int t0 = (int)(r0 / tile_rows), t1 = (int)((r0 + L - 1) / tile_rows);

@@ -143,6 +143,7 @@ encode_tm_kernel(const EncodeArgs a)
                      ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)tm::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();              // barrier init and the TMEM allocation above overlap the previous kernel's tail
     tce_fill_vectors(a, s_vec, tid);
     if (!FULL_E) {      // padding chunks of the raw stages (k >= embed size) are read by the converters but never written
         uint4 *z = reinterpret_cast<uint4 *>(smem + tm::SMEM_RAW_OFF);
@@ -387,8 +388,8 @@ int launch_encode_tm(const EncodeArgs &a, cudaStream_t st)
     C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tm::SMEM_BYTES));
     int grid = a.n_tiles < sms ? a.n_tiles : sms;
     if (grid < 1) grid = 1;
-    kern<<<grid, tm::THREADS, tm::SMEM_BYTES, st>>>(b);
-    C2V_LAUNCH_OK("encode_tm_kernel");
+    C2V_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(tm::THREADS), (size_t)tm::SMEM_BYTES, st, b));
+    C2V_COUNT_LAUNCH();
     return C2V_OK;
 }
 

@@ -2,15 +2,18 @@
 // tensors makes (main.py:166-169 `.to(device)` x4, model.forward main.py:282, torch.max
 // main.py:285, then results read back on the host).
 //
-// Three streams and two staging slots: the int64 index upload of batch i+1 runs on the copy
+// Three streams and kSlots staging slots: the int64 index upload of batch i+1 runs on the copy
 // stream while batch i computes, and the results of batch i drain on the download stream
-// while batch i+1 computes.
+// while batch i+1 computes.  One batch takes upload + compute + download (~225 us at cfg2) from
+// end to end, so two slots cap the rate at ~112 us per batch; four reach max(upload, compute).
 #include <cstring>
 #include <new>
 
 #include "c2v_common.cuh"
 
 using namespace c2v;
+
+static const int kSlots = 4;
 
 struct c2v_session {
     int device;
@@ -28,7 +31,7 @@ struct c2v_session {
         bool busy;
         bool prepped;          // workspaces hold valid weight images (C2V_FLAG_REUSE_PREP)
         int64_t ticket;
-    } slot[2];
+    } slot[kSlots];
     int64_t next_ticket;
 };
 
@@ -56,7 +59,7 @@ int c2v_session_create(int device, const c2v_dims *d, int32_t max_B, int32_t L, 
     C2V_CUDA_OK(cudaStreamCreateWithFlags(&s->s_run, cudaStreamNonBlocking));
     C2V_CUDA_OK(cudaStreamCreateWithFlags(&s->s_down, cudaStreamNonBlocking));
     const size_t n = (size_t)max_B * L;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         c2v_session::Slot &q = s->slot[i];
         q.ws_enc_bytes = c2v_encode_workspace_bytes(d, max_B, L);
         q.ws_lab_bytes = c2v_label_workspace_bytes(d, max_B);
@@ -83,7 +86,7 @@ void c2v_session_destroy(c2v_session *s)
     if (!s) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; ++i) destroy_slot(s->slot[i]);
+    for (int i = 0; i < kSlots; ++i) destroy_slot(s->slot[i]);
     cudaStreamDestroy(s->s_up); cudaStreamDestroy(s->s_run); cudaStreamDestroy(s->s_down);
     delete s;
 }
@@ -100,7 +103,7 @@ int c2v_forward_host_async(c2v_session *s, const c2v_params *p, const int64_t *s
     if (B < 1 || B > s->max_B) { set_error("c2v_forward_host: B=%d not in [1,%d]", B, s->max_B); return C2V_EINVAL; }
     C2V_CUDA_OK(cudaSetDevice(s->device));
     const int64_t t = s->next_ticket;
-    c2v_session::Slot &q = s->slot[t & 1];
+    c2v_session::Slot &q = s->slot[t % kSlots];
     if (q.busy) {   // the slot's previous batch must have fully drained
         C2V_CUDA_OK(cudaEventSynchronize(q.down_done));
         q.busy = false;
@@ -138,9 +141,9 @@ int c2v_forward_host_async(c2v_session *s, const c2v_params *p, const int64_t *s
         C2V_CUDA_OK(cudaMemcpyAsync(outputs, q.d_out, (size_t)B * s->dims.label_count * 4, cudaMemcpyDeviceToHost, s->s_down));
     if (pred_label) C2V_CUDA_OK(cudaMemcpyAsync(pred_label, q.d_pred, (size_t)B * 8, cudaMemcpyDeviceToHost, s->s_down));
     if (pred_score) C2V_CUDA_OK(cudaMemcpyAsync(pred_score, q.d_score, (size_t)B * 4, cudaMemcpyDeviceToHost, s->s_down));
-    C2V_CUDA_OK(cudaMemcpyAsync(q.h_status, q.ws_enc, 8, cudaMemcpyDeviceToHost, s->s_down));
+    C2V_CUDA_OK(cudaMemcpyAsync(q.h_status, static_cast<const char *>(q.ws_enc) + 24, 8, cudaMemcpyDeviceToHost, s->s_down));   // published count
     C2V_CUDA_OK(cudaEventRecord(q.down_done, s->s_down));
-    // (the next upload into this slot's d_idx happens two batches later, after the host has
+    // (the next upload into this slot's d_idx happens kSlots batches later, after the host has
     //  waited on down_done above, so it cannot overtake this batch's kernels)
     q.busy = true;
     q.ticket = t;
@@ -152,7 +155,7 @@ int c2v_forward_host_async(c2v_session *s, const c2v_params *p, const int64_t *s
 int c2v_session_wait(c2v_session *s, int64_t ticket)
 {
     if (!s) { set_error("session is NULL"); return C2V_EINVAL; }
-    c2v_session::Slot &q = s->slot[ticket & 1];
+    c2v_session::Slot &q = s->slot[ticket % kSlots];
     if (q.ticket != ticket) { set_error("ticket %lld is not in flight", (long long)ticket); return C2V_EINVAL; }
     C2V_CUDA_OK(cudaEventSynchronize(q.down_done));
     q.busy = false;

@@ -218,7 +218,9 @@ int64_t c2v_launch_count(void);
  * its dominant kernel (the fused gather+encode+attention kernel, not the weight prep or the
  * per-bag finalize) with CUDA events on the launching stream.  c2v_profile_read synchronises
  * those events and returns the summed kernel milliseconds and the launch count since the last
- * enable; timing never runs under a profiler and adds no device work. */
+ * enable; timing never runs under a profiler and adds no device work.  on > 1 samples every
+ * on-th call only: an event between two launches keeps the second from starting as a
+ * programmatic dependent of the first, so a throughput loop should sample, not bracket every step. */
 int c2v_profile_enable(int32_t on);
 int c2v_profile_read(double *kernel_ms, int64_t *launches);
 
