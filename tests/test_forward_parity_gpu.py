@@ -287,3 +287,61 @@ def test_predict_surface():
     am, mx, cv, att = m.predict(cuda(rec["starts"]), cuda(rec["paths"]), cuda(rec["ends"]))
     assert np.array_equal(am.cpu().numpy(), rec["outputs"].argmax(1))
     assert np.abs(cv.cpu().numpy() - rec["code_vector"]).max() <= EXPECT
+
+
+@pytest.mark.parametrize("name,T,P,E,H", [("cfg5", 2_000_000, 500_000, 128, 128), ("cfg3", 360_633, 342_846, 100, 100)])
+def test_baseline_vocab_sizes_sampled_against_the_oracle(name, T, P, E, H):
+    """BASELINE.json configs[4] (2M terminals / 500K paths: 1.28 GB of tables, every gather misses L2) and configs[2]
+    (top11 vocabulary sizes at the reference's default 100/100/100) at the full 1024 x 200 batch: a sample of bags against
+    the oracle, all rows against the size-independent properties, and the 32-bit row-offset arithmetic at its largest."""
+    from oracle import oracle
+    g = torch.Generator(device="cuda:0").manual_seed(5)
+    B, L, C = 1024, 200, 64
+    emb_t = torch.randn(T, E, generator=g, device="cuda:0"); emb_p = torch.randn(P, E, generator=g, device="cuda:0")
+    rng = np.random.default_rng(11)
+    p = random_params(rng, 8, 8, C, E, E, H)
+    starts = torch.randint(1, T, (B, L), generator=g, device="cuda:0"); paths = torch.randint(1, P, (B, L), generator=g, device="cuda:0")
+    ends = torch.randint(1, T, (B, L), generator=g, device="cuda:0")
+    starts[:, -1] = T - 1; paths[:, -1] = P - 1; ends[0, :] = T - 1           # the last rows of both tables
+    starts[5, 100:] = 0                                                        # a padded suffix
+    dims = CF.make_dims(T, P, C, E, E, H)
+    assert supports_tcgen05(dict(T=T, P=P, C=C, Et=E, Ep=E, H=H))
+    tp = {k: cuda(v) for k, v in p.items()}
+    params = CF.make_params(emb_t, emb_p, tp["input_linear.weight"], tp["input_layer_norm.weight"],
+                            tp["input_layer_norm.bias"], tp["attention_parameter"])
+    cv, att = CF.encode_forward(dims, params, starts, paths, ends, algo=_lib.ALGO_TCGEN05, check_indices=True)
+    a = att.cpu().numpy(); v = cv.cpu().numpy()
+    assert np.allclose(a.sum(1), 1.0, atol=2e-5) and (a >= 0).all() and np.abs(v).max() <= 1.0 + 1e-6
+    assert (a[5, 100:] == 0).all()
+    sel = np.array([0, 5, 17, 511, 1023])
+    sn, pn, en = starts[sel].cpu().numpy(), paths[sel].cpu().numpy(), ends[sel].cpu().numpy()
+    # compact the sampled bags' rows so that the scalar oracle does not need the whole table on the host
+    ut, it = np.unique(np.concatenate([sn.ravel(), en.ravel()]), return_inverse=True)
+    up, ip = np.unique(pn.ravel(), return_inverse=True)
+    et_small = emb_t[torch.from_numpy(ut).cuda()].cpu().numpy(); ep_small = emb_p[torch.from_numpy(up).cuda()].cpu().numpy()
+    s2 = it[:sn.size].reshape(sn.shape).astype(np.int64); e2 = it[sn.size:].reshape(en.shape).astype(np.int64)
+    p2 = ip.reshape(pn.shape).astype(np.int64)
+    # index 0 means padding to the mask (model.py:64): keep real rows away from compact index 0
+    et_small = np.concatenate([emb_t[:1].cpu().numpy(), et_small]); ep_small = np.concatenate([emb_p[:1].cpu().numpy(), ep_small])
+    s2 = np.where(sn == 0, 0, s2 + 1); e2 = np.where(en == 0, 0, e2 + 1); p2 = np.where(pn == 0, 0, p2 + 1)
+    ref_cv, ref_att = oracle.encode_forward(s2, p2, e2, et_small, ep_small, p["input_linear.weight"],
+                                            p["input_layer_norm.weight"], p["input_layer_norm.bias"], p["attention_parameter"])
+    assert np.abs(v[sel] - ref_cv).max() <= EXPECT and np.abs(a[sel] - ref_att).max() <= EXPECT
+
+
+def test_fused_argmax_at_top11_label_count():
+    """configs[2]'s label vocabulary (C = 195,299: odd, so output rows are only 4-byte aligned; 800 MB of logits at
+    B = 1024): logits against the CUDA-core GEMM on a row sample, arg-max against torch.max on all rows."""
+    B, C, H = 1024, 195_299, 100
+    g = torch.Generator(device="cuda:0").manual_seed(9)
+    cvt = torch.tanh(torch.randn(B, H, generator=g, device="cuda:0"))
+    w = torch.randn(C, H, generator=g, device="cuda:0") * 0.2
+    w[C - 1] = w[3]                                    # exact tie between class 3 and the last class
+    bias = torch.randn(C, generator=g, device="cuda:0") * 0.05; bias[C - 1] = bias[3]
+    dims = CF.make_dims(10, 10, C, H, H, H)
+    params = CF.make_params(None, None, None, None, None, None, w, bias)
+    out, am, mx = CF.label_logits_argmax(dims, params, cvt, algo=_lib.ALGO_AUTO)
+    tv, ti = torch.max(out, dim=1)
+    assert torch.equal(mx, tv) and torch.equal(am, ti)
+    ref = cvt[:64].double() @ w.double().T + bias.double()
+    assert (out[:64].double() - ref).abs().max().item() <= 3e-6 * max(1.0, ref.abs().max().item())
