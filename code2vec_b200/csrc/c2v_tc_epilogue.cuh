@@ -27,16 +27,20 @@ __device__ __forceinline__ void tce_fill_vectors(const EncodeArgs &a, float *s_v
     }
 }
 
-// One tile of one epilogue thread: row `row` of the tile, columns [hf * HC, hf * HC + HCV) of the accumulator
-// (HCV <= HC valid columns: the rest is padding of an encode_size < 128 and is neither read into the LayerNorm
-// moments nor written anywhere).
-template <bool DROPOUT, int NS, int HC, int HCV>
+// One tile of one epilogue thread: row `row` of the tile, columns [hf * HC, hf * HC + HC) of the accumulator.
+// The NS slices of a row are equally wide (HC = 64 at encode_size 128, 52 at 100), so all epilogue warps run the same
+// code for the same time; columns >= a.H (only in the last 4-column group of the last slice) are padding: their
+// accumulators are exactly 0 (zero rows of the W image), gamma' = beta' = attn = 0 makes their tanh output 0, `vlast`
+// (0 or 1) removes them from the variance, and they are not written anywhere.
+template <bool DROPOUT, int NS, int HC>
 __device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *s_vec, float *my_x, const float *qx,
-                                              float (&x)[HC], int q, int hf, int lane, long long vrow0, long long row,
-                                              bool in_range, long long st_idx, float inv_scale, float inv_h)
+                                              float (&x)[(HC + 31) / 32 * 32], int q, int hf, int lane, long long vrow0,
+                                              long long row, bool in_range, long long st_idx, float inv_scale,
+                                              float inv_h, float vlast, int n_valid)
 {
     namespace tc = tce;
-    static_assert(HCV % 4 == 0 && HCV >= 4 && HCV <= HC, "valid columns per slice");
+    static_assert(HC % 4 == 0 && HC >= 4, "columns per slice");
+    constexpr int HCR = (HC + 31) / 32 * 32;                    // rounded up to whole 32-column butterfly groups
     const float4 *sG = reinterpret_cast<const float4 *>(s_vec + hf * HC);
     const float4 *sB = reinterpret_cast<const float4 *>(s_vec + tc::H + hf * HC);
     const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * tc::H + hf * HC);
@@ -49,16 +53,20 @@ __device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *
     // LayerNorm (model.py:55-56), two-pass; x is scale * (c . W^T); slices exchanged via smem
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int c = 0; c < HCV; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
+    for (int c = 0; c < HC; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
     float part = (s0 + s1) + (s2 + s3);
     my_x[0] = part;
     named_bar_sync(1 + q, 32 * NS);
     const float mean = xsum(0) * inv_h;
     s0 = s1 = s2 = s3 = 0.f;
 #pragma unroll
-    for (int c = 0; c < HCV; c += 4) {
+    for (int c = 0; c < HC - 4; c += 4) {
         const float d0 = x[c] - mean, d1 = x[c + 1] - mean, d2 = x[c + 2] - mean, d3 = x[c + 3] - mean;
         s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+    }
+    {
+        const float d0 = x[HC - 4] - mean, d1 = x[HC - 3] - mean, d2 = x[HC - 2] - mean, d3 = x[HC - 1] - mean;
+        s0 = fmaf(d0 * vlast, d0, s0); s1 = fmaf(d1 * vlast, d1, s1); s2 = fmaf(d2 * vlast, d2, s2); s3 = fmaf(d3 * vlast, d3, s3);
     }
     part = (s0 + s1) + (s2 + s3);
     my_x[32] = part;
@@ -69,7 +77,7 @@ __device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *
     // tanh (model.py:57), dropout (model.py:60-61), score h.a (model.py:92-93)
     float u0 = 0.f, u1 = 0.f;
 #pragma unroll
-    for (int c4 = 0; c4 < HCV / 4; ++c4) {
+    for (int c4 = 0; c4 < HC / 4; ++c4) {
         const float4 g = sG[c4], b = sB[c4], at = sA[c4];
         float y0 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 0], nrm, shift), g.x, b.x));
         float y1 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 1], nrm, shift), g.y, b.y));
@@ -87,7 +95,7 @@ __device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *
         u0 = fmaf(y2, at.z, u0); u1 = fmaf(y3, at.w, u1);
     }
 #pragma unroll
-    for (int c = HCV; c < (HCV + 31) / 32 * 32; ++c) x[c] = 0.0f;     // padding inside the last 32-column group
+    for (int c = HC; c < HCR; ++c) x[c] = 0.0f;                 // fill the last 32-column butterfly group
     part = u0 + u1;
     my_x[64] = part;
     named_bar_sync(1 + q, 32 * NS);
@@ -109,12 +117,12 @@ __device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *
             const size_t slot = (size_t)(vt + bag);
             float *pv = a.ws.part_v + slot * a.H + hf * HC;
 #pragma unroll
-            for (int c = 0; c < (HCV + 31) / 32; ++c) {
+            for (int c = 0; c < HCR / 32; ++c) {
                 float t[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) t[j] = e * x[c * 32 + j];
                 butterfly_reduce32(t, lane);
-                if (c * 32 + lane < HCV) pv[c * 32 + lane] = t[0];
+                if (c * 32 + lane < n_valid) pv[c * 32 + lane] = t[0];
             }
             if (hf == 0) {
                 const float ssum = warp_sum(e);
@@ -124,14 +132,14 @@ __device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *
     }
 }
 
-// Runs on warps 0..7 (warp q and q+4 share TMEM lane quarter q and split the 128 columns).
+// Runs on warps 0..7 (warp q and q+4 share TMEM lane quarter q and split the columns).
 // tile(tl) = blockIdx.x + tl * gridDim.x; accumulator stage tl & 1 at tmem_base + (tl & 1) * 128.
 // DROPOUT is a template parameter so the eval instantiation carries no Philox code: the unrolled epilogue
 // shrinks from ~3000 to ~1500 SASS instructions (it was missing the instruction cache, 16 % stall_no_inst).
 // NS = column slices per lane quarter (epilogue warps = 4 * NS): warp w handles rows of quarter w & 3 and
-// columns [(w >> 2) * H/NS, ...); LayerNorm moments and the score are summed across the NS warps of a
+// columns [(w >> 2) * HC, ...); LayerNorm moments and the score are summed across the NS warps of a
 // quarter through smem + a named barrier, always in slice order so every warp gets the same bits.
-// HV = encode_size (valid accumulator columns, multiple of 4, > (NS-1) * 128/NS); the tile is always 128 wide.
+// HV = encode_size (multiple of 4); the accumulator tile is always 128 wide, HC = ceil4(HV / NS) columns per slice.
 template <bool DROPOUT, int NS = 2, int HV = 128>
 __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_vec, float *s_xch,
                                                   uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
@@ -140,9 +148,12 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
     namespace tc = tce;
         const int q = warp & 3;                 // TMEM lane quarter: rows 32q .. 32q+31 of the tile
         const int hf = warp >> 2;               // column slice: HC*hf .. HC*hf+HC-1
-        constexpr int HC = tc::H / NS;          // columns per thread (64 or 32)
-        constexpr int HC_LAST = HV - (NS - 1) * HC;      // valid columns of the last slice
-        static_assert(HC_LAST > 0 && HC_LAST <= HC, "encode_size must reach into the last column slice");
+        constexpr int HC = ((HV + NS - 1) / NS + 3) / 4 * 4;     // columns per thread (64 at 128, 52 at 100)
+        constexpr int HCR = (HC + 31) / 32 * 32;
+        static_assert(NS * HC <= tc::H && NS * HC - HV <= 4, "padding stays inside the last 4-column group of the last slice");
+        static_assert(HC % 32 == 0 || HC % 32 == 16 + 4 || HC % 32 == 16 || HC % 32 == 4, "TMEM load shapes: x32, x16, x4");
+        const int n_valid = (HV - hf * HC) < HC ? (HV - hf * HC) : HC;   // valid columns of this slice
+        const float vlast = n_valid == HC ? 1.0f : 0.0f;
         const float inv_scale = a.ws.prep_hdr[0];
         float *my_x = s_xch + ((q * NS + hf) * 3) * 32 + lane;          // [3][32] per (quarter, slice)
         const float *qx = s_xch + (q * NS * 3) * 32 + lane;             // slice s, slot k at qx[(s*3+k)*32]
@@ -157,22 +168,20 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
 
             mbar_wait(bar_tfull + 8 * acc, acc_phase, status);
             tc_fence_after();
-            float x[HC];
+            float x[HCR];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * tc::H + hf * HC);
 #pragma unroll
             for (int c = 0; c < HC / 32; ++c) tmem_ld32(taddr + c * 32, x + c * 32);
+            if (HC % 32 >= 16) tmem_ld16(taddr + HC / 32 * 32, x + HC / 32 * 32);
+            if (HC % 16 == 4) tmem_ld4(taddr + HC / 16 * 16, x + HC / 16 * 16);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);           // accumulator is free again
             if (a.flags & 16) continue;        // timing experiment: producer side alone (results are wrong)
 
-            if (HC_LAST == HC || hf < NS - 1)
-                tce_tile_body<DROPOUT, NS, HC, HC>(a, s_vec, my_x, qx, x, q, hf, lane, vrow0, row, in_range, st_idx,
-                                                   inv_scale, 1.0f / (float)HV);
-            else
-                tce_tile_body<DROPOUT, NS, HC, HC_LAST>(a, s_vec, my_x, qx, x, q, hf, lane, vrow0, row, in_range, st_idx,
-                                                        inv_scale, 1.0f / (float)HV);
+            tce_tile_body<DROPOUT, NS, HC>(a, s_vec, my_x, qx, x, q, hf, lane, vrow0, row, in_range, st_idx,
+                                           inv_scale, 1.0f / (float)HV, vlast, n_valid);
         }
 }
 
