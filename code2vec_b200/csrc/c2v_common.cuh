@@ -37,6 +37,14 @@ extern long long g_launches;
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Timing experiments (skip a role's work to see what the others cost; results become wrong) exist only in builds
+// with -DC2V_EXPERIMENTS (C2V_NVCC_EXTRA=-DC2V_EXPERIMENTS python -m code2vec_b200.build); product builds compile them out.
+#ifdef C2V_EXPERIMENTS
+#define C2V_EXPT(flags, bit) (((flags) & (bit)) != 0)
+#else
+#define C2V_EXPT(flags, bit) false
+#endif
+
 #ifdef __CUDACC__
 // Programmatic dependent launch: the kernel may start (prologue, block scheduling) while the previous kernel of the
 // stream is still draining; it must execute griddepcontrol.wait (pdl_wait()) before touching anything the previous

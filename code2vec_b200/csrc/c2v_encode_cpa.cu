@@ -137,7 +137,7 @@ encode_cpa_kernel(const EncodeArgs a)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_rempty + 8 * st);
                 mbar_wait(bar_oempty + 8 * st, phase ^ 1u, status);       // MMAs of the previous use retired
-                if (!(a.flags & 32))               // (timing experiment: skip the conversion + stores)
+                if (!C2V_EXPT(a.flags, 32))         // (timing experiment: skip the conversion + stores)
 #pragma unroll
                 for (int j = 0; j < ca::LDS_PER_ITEM; ++j) {
                     const __half2 h01 = __floats2half2_rn(v[j].x, v[j].y), h23 = __floats2half2_rn(v[j].z, v[j].w);
@@ -195,7 +195,7 @@ encode_cpa_kernel(const EncodeArgs a)
                     cp_async_cg16(dst + j * 2 * (ca::KB * 4), tab + o);
                 }
                 cp_async_mbar_arrive_noinc(bar_rfull + 8 * st);
-                if (!(a.flags & 2)) {
+                if (C2V_EXPT(a.flags, 2)) {      // (experiment, off by default: measured slower)
                     // Only two raw stages (64 KB) can be in flight per SM, which at HBM latency caps the kernel
                     // (profiles/README.md).  Pull the half rows of item +2 -- the one that cannot be issued yet --
                     // towards L2 now: this lane's own row, two 128-B lines.
@@ -239,8 +239,8 @@ encode_cpa_kernel(const EncodeArgs a)
                             const uint64_t w_hi = umma_desc(sa + 2 * ca::TILE_BYTES + k * 32);
                             const uint64_t w_lo = umma_desc(sa + 3 * ca::TILE_BYTES + k * 32);
                             umma_f16(d_tmem, a_hi, w_hi, ca::IDESC, (kb | k) != 0 ? 1u : 0u);
-                            if (!(a.flags & 4)) umma_f16(d_tmem, a_lo, w_hi, ca::IDESC, 1u);
-                            if (!(a.flags & 8)) umma_f16(d_tmem, a_hi, w_lo, ca::IDESC, 1u);
+                            if (!C2V_EXPT(a.flags, 4)) umma_f16(d_tmem, a_lo, w_hi, ca::IDESC, 1u);
+                            if (!C2V_EXPT(a.flags, 8)) umma_f16(d_tmem, a_hi, w_lo, ca::IDESC, 1u);
                         }
                         umma_commit(bar_oempty + 8 * st);
                     }

@@ -177,7 +177,7 @@ encode_tm_kernel(const EncodeArgs a)
             TM_WAIT(bar_rfull + 8 * st, phase, 1);                 // gathered fp32 rows have landed
             float4 v[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[c] = (a.flags & 128) ? make_float4(0.f, 0.f, 0.f, 0.f) : tm_lds_v4(rawb + ld_off[c]);
+            for (int c = 0; c < 8; ++c) v[c] = C2V_EXPT(a.flags, 128) ? make_float4(0.f, 0.f, 0.f, 0.f) : tm_lds_v4(rawb + ld_off[c]);
             // the asm volatile loads above complete in order before this arrive: the raw stage can be
             // refilled by the next gather while this warp converts out of registers
             __syncwarp();
@@ -203,7 +203,7 @@ encode_tm_kernel(const EncodeArgs a)
                     TM_WAIT(bar_aempty + 8 * as, aphase ^ 1u, 2);          // MMAs of the previous use retired
                     tc_fence_after();
                 }
-                if (!(a.flags & 32)) {             // (timing experiment: skip the TMEM stores)
+                if (!C2V_EXPT(a.flags, 32)) {      // (timing experiment: skip the TMEM stores)
                     tmem_st8(t_st + g * 8, hi);
                     tmem_st8(t_st + tm::KB / 2 + g * 8, lo);
                 }
@@ -272,7 +272,7 @@ encode_tm_kernel(const EncodeArgs a)
                     for (int j = 0; j < tm::CPA_PER_ITEM; ++j) {
                         const uint32_t chunk = (uint32_t)(h * tm::RAW_ROW_BYTES) + qoff[j & 3];   // byte offset in the row
                         if (FULL_E) {
-                            if (!(a.flags & 64)) tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o[j] + chunk));
+                            if (!C2V_EXPT(a.flags, 64)) tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o[j] + chunk));
                         } else if (chunk < row_bytes) {     // chunk positions at or beyond the embedding size are never
                             tm_cp_async_cg16(dst + j * 2 * tm::RAW_ROW_BYTES, tab + (o[j] + chunk));   // written: zero since start
                         }

@@ -287,7 +287,7 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
                 v[j] = fmaf(__uint_as_float(r[j]), inv_scale, b4.x); v[j + 1] = fmaf(__uint_as_float(r[j + 1]), inv_scale, b4.y);
                 v[j + 2] = fmaf(__uint_as_float(r[j + 2]), inv_scale, b4.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), inv_scale, b4.w);
             }
-            if (want_arg && lane < n_rows && n_cols > 0 && !(dbg & 2)) {
+            if (want_arg && lane < n_rows && n_cols > 0 && !C2V_EXPT(dbg, 2)) {
                 float m = -INFINITY;
                 if (n_cols == 32) {
 #pragma unroll
@@ -310,12 +310,12 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
             for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4 *>(stg + lane * lt2::STG_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             __syncwarp();
-            if (dbg & 4) {          // timing experiment: same bytes, but every warp block as one contiguous 4 KB run
+            if (C2V_EXPT(dbg, 4)) {          // timing experiment: same bytes, but every warp block as one contiguous 4 KB run
                 float *gp = out + ((size_t)(t_lo + i) * 16 + warp) * 1024 + lane * 4;
 #pragma unroll
                 for (int it = 0; it < 8; ++it)
                     *reinterpret_cast<float4 *>(gp + it * 128) = *reinterpret_cast<const float4 *>(stg + (it * 4 + (lane >> 3)) * lt2::STG_LD + (lane & 7) * 4);
-            } else if (n_rows > 0 && n_cols > 0 && !(dbg & 1)) {
+            } else if (n_rows > 0 && n_cols > 0 && !C2V_EXPT(dbg, 1)) {
                 if (vec_ok && n_cols == 32) {
                     const int rr0 = lane >> 3, c4 = (lane & 7) * 4;          // 4 rows x 128 B per store instruction
                     float *gp = out + (size_t)(row0 + rr0) * N + col0 + c4;

@@ -178,7 +178,7 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);           // accumulator is free again
-            if (a.flags & 16) continue;        // timing experiment: producer side alone (results are wrong)
+            if (C2V_EXPT(a.flags, 16)) continue;        // timing experiment: producer side alone (results are wrong)
 
             tce_tile_body<DROPOUT, NS, HC>(a, s_vec, my_x, qx, x, q, hf, lane, vrow0, row, in_range, st_idx,
                                            inv_scale, 1.0f / (float)HV, vlast, n_valid);
