@@ -40,6 +40,10 @@ WORKLOADS = {
     "cfg3": dict(T=360633, P=342846, C=195299, Et=100, Ep=100, H=100, B=1024, L=200,
                  desc="top11_dataset sizes: T=360,633 P=342,846 C=195,299, embed=100/100, encode=100, batch=1024 "
                       "(synthetic uniform indices; the corpus itself is not shipped)"),
+    # configs[3]: embed=encode=256, global batch 4096 over 8 GPUs = 512 per rank (the per-rank shard is what one GPU runs)
+    "cfg4": dict(T=360633, P=342846, C=8192, Et=256, Ep=256, H=256, B=512, L=200,
+                 desc="synthetic methods x 200 contexts, embed=256/256, encode=256, batch=512 per GPU (4096 over 8), "
+                      "top11-sized vocab, C=8,192"),
     # small variant for quick functional runs
     "tiny": dict(T=5000, P=4000, C=256, Et=128, Ep=128, H=128, B=64, L=200, desc="tiny functional run"),
 }

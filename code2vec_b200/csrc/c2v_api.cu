@@ -91,7 +91,9 @@ EncodeWorkspace carve_encode_workspace(const c2v_dims *d, int B, int L, void *ba
     const size_t n_tiles = (size_t)((N + kMinTileRows - 1) / kMinTileRows);
     const size_t slots = n_tiles + (size_t)B + 1;
     // tcgen05 split weights: K padded to 64-element blocks, N padded to 128 rows... sized generously
-    const size_t kblocks = (size_t)(D + 63) / 64 + 3;          // +3: per-sub-vector padding
+    size_t kblocks = (size_t)(D + 63) / 64 + 3;                // +3: per-sub-vector padding
+    const size_t padded = (H > 128 || d->terminal_embed > 128) ? 12 : 6;   // K1e pads each sub-vector to 128 / 256 k
+    if (kblocks < padded) kblocks = padded;
     const size_t hp = (size_t)(H + 127) / 128 * 128;
     char *p = static_cast<char *>(base);
     size_t o = 0;

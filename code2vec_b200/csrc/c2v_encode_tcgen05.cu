@@ -61,36 +61,40 @@ constexpr float TWO_LOG2E = 2.8853900817779268f;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
 }  // namespace tc
 
-// K1e (c2v_encode_tm.cu) pads every sub-vector to 128 k and the encode size to 128 columns, so it also serves
-// the reference's default 100/100/100 (main.py:56-58): terminal_embed == path_embed = E, E % 4 == 0, E <= 128,
-// encode_size in {100, 128}.  Row offsets are 32-bit inside the kernels: tables up to 4 GB.
+// K1e (c2v_encode_tm.cu) pads every sub-vector and the encode size to 128 -- or to 256 in its wide configuration --
+// so it serves the reference's default 100/100/100 (main.py:56-58) and BASELINE.json's 256/256/256 as well:
+// terminal_embed == path_embed = E, E % 4 == 0; (E <= 128 and encode_size in {100, 128}) or (E <= 256 and encode_size
+// == 256).  Row offsets are 32-bit inside the kernels: tables up to 4 GB.
+static bool tm_wide(int E, int H) { return H > tc::H || E > tc::E; }
 bool tcgen05_shape_ok(const c2v_dims *d)
 {
-    const int E = d->terminal_embed;
-    if (d->path_embed != E || E < 4 || E > tc::E || (E & 3)) return false;
-    if (d->encode != 100 && d->encode != tc::H) return false;
+    const int E = d->terminal_embed, H = d->encode;
+    if (d->path_embed != E || E < 4 || (E & 3)) return false;
+    const bool narrow = E <= 128 && (H == 100 || H == 128), wide = E <= 256 && H == 256;
+    if (!narrow && !wide) return false;
     const long long row_bytes = (long long)E * 4;
     return d->terminal_count * row_bytes < (1ll << 32) && d->path_count * row_bytes < (1ll << 32);
 }
 
 // ------------------------------------------------------------------------------------
-// weight preparation: W [H, 3E] fp32 -> 6 k-block images {hi tile, lo tile} of [128 n x 64 k] fp16 in the exact
-// shared-memory layout, scaled by 2^k.  Sub-vector sv (start / path / end) owns k-blocks 2sv, 2sv+1; k >= E and
-// n >= H are zero padding.  One CTA; <= 49 K elements.
+// weight preparation: W [H, 3E] fp32 -> 3*NQ k-block images {hi tile, lo tile} of [HP n x 64 k] fp16 in the exact
+// shared-memory layout (K-major SWIZZLE_128B), scaled by 2^k; EP = HP = 128 (NQ = 2) or 256 (NQ = 4).  Sub-vector sv
+// (start / path / end) owns k-blocks NQ*sv .. NQ*sv + NQ-1; k >= E and n >= H are zero padding.  One CTA.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__restrict__ hdr, int E, int H)
+split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__restrict__ hdr, int E, int H, int EP, int HP)
 {
     __shared__ float red[32];
     const int tid = threadIdx.x;
-    const int D = 3 * E;
+    const int D = 3 * E, NQ = EP / tc::KB;
+    const int tile_bytes = HP * tc::KB * 2, kb_bytes = 2 * tile_bytes;
     float mx = 0.0f;
     for (int i = tid; i < H * D; i += 1024) mx = fmaxf(mx, fabsf(W[i]));
     mx = warp_max(mx);
     if ((tid & 31) == 0) red[tid >> 5] = mx;
-    if (E < tc::E || H < tc::H) {                            // zero padding of the image
+    if (E < EP || H < HP) {                                  // zero padding of the image
         uint4 *z = reinterpret_cast<uint4 *>(img);
-        for (int i = tid; i < tc::NKB * tc::W_KB_BYTES / 16; i += 1024) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < 3 * NQ * kb_bytes / 16; i += 1024) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
     mx = red[0];
@@ -111,17 +115,18 @@ split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__
         const float w = W[i] * scale;
         const __half hi = __float2half_rn(w);
         const __half lo = __float2half_rn(w - __half2float(hi));
-        const int kb = 2 * sv + e / tc::KB, kk = e % tc::KB;
-        uint8_t *base = img + (size_t)kb * tc::W_KB_BYTES;
+        const int kb = NQ * sv + e / tc::KB, kk = e % tc::KB;
+        uint8_t *base = img + (size_t)kb * kb_bytes;
         const uint32_t off = sw128_offset(n, kk);
         *reinterpret_cast<__half *>(base + off) = hi;
-        *reinterpret_cast<__half *>(base + tc::TILE_BYTES + off) = lo;
+        *reinterpret_cast<__half *>(base + tile_bytes + off) = lo;
     }
 }
 
 int launch_split_w_tcgen05(const c2v_dims *d, const float *W, EncodeWorkspace &ws, cudaStream_t st)
 {
-    split_w_kernel<<<1, 1024, 0, st>>>(W, reinterpret_cast<uint8_t *>(ws.w_hi), ws.prep_hdr, d->terminal_embed, d->encode);
+    const int P = tm_wide(d->terminal_embed, d->encode) ? 256 : 128;
+    split_w_kernel<<<1, 1024, 0, st>>>(W, reinterpret_cast<uint8_t *>(ws.w_hi), ws.prep_hdr, d->terminal_embed, d->encode, P, P);
     C2V_LAUNCH_OK("split_w_kernel");
     return C2V_OK;
 }

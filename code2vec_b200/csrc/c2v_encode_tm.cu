@@ -21,34 +21,42 @@
 
 namespace c2v {
 
-namespace tm {
-constexpr int ROWS = tce::ROWS, H = tce::H, E = 128, D = 3 * E;
-constexpr int KB = 64, NKB = D / KB;                  // 6 k-blocks per tile
-constexpr int RAW_STAGES = 4, W_STAGES = 2, A_STAGES = 4;
-constexpr int RAW_ROW_BYTES = KB * 4;                 // 256 B: half an embedding row
-constexpr int RAW_BYTES = ROWS * RAW_ROW_BYTES;       // 32 KB
-constexpr int TILE_BYTES = ROWS * KB * 2;             // 16 KB fp16 tile
-constexpr int W_KB_BYTES = 2 * TILE_BYTES;            // {hi, lo} of one k-block of W
-constexpr int N_CONV_WARPS = 8;
-constexpr int CONV_WARP0 = tce::N_EPI_WARPS;          // 8 (multiple of 4: warp & 3 is the TMEM lane quarter)
-constexpr int N_LOAD_WARPS = 4;
-constexpr int LOAD_WARP0 = CONV_WARP0 + N_CONV_WARPS; // 16
-constexpr int MISC_WARP0 = LOAD_WARP0 + N_LOAD_WARPS; // 20
-constexpr int THREADS = (MISC_WARP0 + 4) * 32;        // 768: warps 22-23 only donate their registers (setmaxnreg pool)
-constexpr int CPA_PER_ITEM = ROWS / N_LOAD_WARPS / 2; // 16 x LDGSTS.128 (two 256-B half rows per instruction)
-constexpr int TMEM_COLS = 512;
-constexpr int A_COL0 = 2 * H;                         // first A-stage column
-constexpr int A_STAGE_COLS = KB;                      // hi: KB/2 columns, lo: KB/2 columns
-constexpr int SMEM_RAW_OFF = 0;
-constexpr int SMEM_W_OFF = RAW_STAGES * RAW_BYTES;
-constexpr int SMEM_VEC_OFF = SMEM_W_OFF + W_STAGES * W_KB_BYTES;
-constexpr int SMEM_XCH_OFF = SMEM_VEC_OFF + tce::VEC_BYTES;
-constexpr int SMEM_BAR_OFF = SMEM_XCH_OFF + tce::XCH_BYTES;
-constexpr int SMEM_BYTES = SMEM_BAR_OFF + 256 + 1024;
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-static_assert((RAW_STAGES & (RAW_STAGES - 1)) == 0 && (A_STAGES & (A_STAGES - 1)) == 0 && W_STAGES == 2, "ring index math");
-static_assert(A_COL0 + A_STAGES * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
-}  // namespace tm
+// WIDE = false: terminal_embed = path_embed <= 128, encode_size 100 / 128 (two 128-column accumulators, 4 x 32 KB
+// gather stages).  WIDE = true: embed <= 256, encode_size 256 (BASELINE.json configs[3]): one 256-column accumulator
+// (UMMA N = 256), 64 KB W k-blocks, 2 gather stages; tensor-bound (393 K FLOP per context x 3 passes).
+template <bool WIDE>
+struct TmCfg {
+    static constexpr int ROWS = tce::ROWS;
+    static constexpr int EP = WIDE ? 256 : 128;              // padded sub-vector width (k per start / path / end)
+    static constexpr int HP = WIDE ? 256 : 128;              // padded encode size = UMMA N
+    static constexpr int KB = 64, NQ = EP / KB, NKB = 3 * NQ; // k-blocks per sub-vector / per tile
+    static constexpr int RAW_STAGES = WIDE ? 2 : 4, W_STAGES = 2, A_STAGES = 4, ACC_STAGES = WIDE ? 1 : 2;
+    static constexpr int RAW_ROW_BYTES = KB * 4;             // 256 B of an embedding row
+    static constexpr int RAW_BYTES = ROWS * RAW_ROW_BYTES;   // 32 KB
+    static constexpr int TILE_BYTES = HP * KB * 2;           // one fp16 W tile [HP n x 64 k]: 16 / 32 KB
+    static constexpr int W_KB_BYTES = 2 * TILE_BYTES;        // {hi, lo} of one k-block of W
+    static constexpr int N_CONV_WARPS = 8;
+    static constexpr int CONV_WARP0 = tce::N_EPI_WARPS;      // 8 (multiple of 4: warp & 3 is the TMEM lane quarter)
+    static constexpr int N_LOAD_WARPS = 4;
+    static constexpr int LOAD_WARP0 = CONV_WARP0 + N_CONV_WARPS; // 16
+    static constexpr int MISC_WARP0 = LOAD_WARP0 + N_LOAD_WARPS; // 20
+    static constexpr int THREADS = (MISC_WARP0 + 4) * 32;    // 768: warps 22-23 only donate their registers (setmaxnreg pool)
+    static constexpr int CPA_PER_ITEM = ROWS / N_LOAD_WARPS / 2; // 16 x LDGSTS.128 (two 256-B row pieces per instruction)
+    static constexpr int TMEM_COLS = 512;
+    static constexpr int A_COL0 = ACC_STAGES * HP;           // first A-stage column (256)
+    static constexpr int A_STAGE_COLS = KB;                  // hi: KB/2 columns, lo: KB/2 columns
+    static constexpr int VEC_BYTES = 3 * HP * 4;             // gamma' | beta' | attn
+    static constexpr int SMEM_RAW_OFF = 0;
+    static constexpr int SMEM_W_OFF = RAW_STAGES * RAW_BYTES;
+    static constexpr int SMEM_VEC_OFF = SMEM_W_OFF + W_STAGES * W_KB_BYTES;
+    static constexpr int SMEM_XCH_OFF = SMEM_VEC_OFF + VEC_BYTES;
+    static constexpr int SMEM_BAR_OFF = SMEM_XCH_OFF + tce::XCH_BYTES;
+    static constexpr int SMEM_BYTES = SMEM_BAR_OFF + 256 + 1024;
+    static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(HP >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+    static_assert((RAW_STAGES & (RAW_STAGES - 1)) == 0 && (A_STAGES & (A_STAGES - 1)) == 0 && W_STAGES == 2, "ring index math");
+    static_assert(A_COL0 + A_STAGES * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
 
 __device__ __forceinline__ void tm_cp_async_cg16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -91,11 +99,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 #define TM_REPORT(slot) do { } while (0)
 #endif
 
-// FULL_E: terminal_embed = path_embed = 128 (no padding chunks); HV = encode_size (100 or 128).
+// FULL_E: terminal_embed = path_embed = EP (no padding chunks); HV = encode_size (100, 128 or 256).
 template <bool DROPOUT, bool FULL_E, int HV>
-__global__ void __launch_bounds__(tm::THREADS, 1)
+__global__ void __launch_bounds__(TmCfg<(HV > 128)>::THREADS, 1)
 encode_tm_kernel(const EncodeArgs a)
 {
+    constexpr bool WIDE = HV > 128;
+    using tm = TmCfg<WIDE>;
 #ifdef TM_INSTRUMENT
     long long tm_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long tm_t_start = clock64();
@@ -133,7 +143,7 @@ encode_tm_kernel(const EncodeArgs a)
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_wfull + 8 * s, 1);
             mbar_init(bar_wempty + 8 * s, 1);
-            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tfull + 8 * s, 1);                  // (WIDE uses stage 0 only)
             mbar_init(bar_tempty + 8 * s, tce::N_EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -144,7 +154,7 @@ encode_tm_kernel(const EncodeArgs a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     pdl_wait();              // barrier init and the TMEM allocation above overlap the previous kernel's tail
-    tce_fill_vectors(a, s_vec, tid);
+    tce_fill_vectors<tm::HP>(a, s_vec, tid);
     if (!FULL_E) {      // padding chunks of the raw stages (k >= embed size) are read by the converters but never written
         uint4 *z = reinterpret_cast<uint4 *>(smem + tm::SMEM_RAW_OFF);
         for (int i = tid; i < tm::RAW_STAGES * tm::RAW_BYTES / 16; i += tm::THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -158,7 +168,10 @@ encode_tm_kernel(const EncodeArgs a)
     if (warp < tce::N_EPI_WARPS) {
         // =============================== EPILOGUE ===============================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-        tce_epilogue_loop<DROPOUT, 2, HV>(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
+        if constexpr (WIDE)
+            tce_epilogue_loop_wide<DROPOUT>(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
+        else
+            tce_epilogue_loop<DROPOUT, 2, HV>(a, s_vec, s_xch, tmem_base, bar_tfull, bar_tempty, warp, lane, my_tiles, status);
     } else if (warp < tm::LOAD_WARP0) {
         // =============================== CONVERTERS ===============================
         // thread = one context row (TMEM lane) x 32 consecutive k of the k-block (8 x LDS.128, conflict-free
@@ -229,7 +242,7 @@ encode_tm_kernel(const EncodeArgs a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) qoff[c] = (uint32_t)(((q ^ sub) ^ (2 * c)) << 4);
         const uint32_t dst_lane = (uint32_t)((lw * 32 + sub) * tm::RAW_ROW_BYTES + q * 16);
-        const uint32_t row_bytes = FULL_E ? (uint32_t)(tm::E * 4) : (uint32_t)(a.Et * 4);     // Et == Ep
+        const uint32_t row_bytes = FULL_E ? (uint32_t)(tm::EP * 4) : (uint32_t)(a.Et * 4);    // Et == Ep
         long long rs = 0, rp = 0, re = 0;            // raw indices of the NEXT tile (prefetched)
         uint32_t off_s = 0, off_p = 0, off_e = 0;    // byte offsets of this lane's row in the tables
         auto fetch_idx = [&](int tl) {
@@ -263,7 +276,7 @@ encode_tm_kernel(const EncodeArgs a)
 #pragma unroll
                 for (int j = 0; j < tm::CPA_PER_ITEM; ++j) o[j] = __shfl_sync(0xffffffffu, off, 2 * j + sub);
 #pragma unroll
-                for (int h = 0; h < 2; ++h, ++it) {
+                for (int h = 0; h < tm::NQ; ++h, ++it) {
                     const int st = it & (tm::RAW_STAGES - 1);
                     const uint32_t phase = (uint32_t)(it / tm::RAW_STAGES) & 1u;
                     const uint32_t dst = base + tm::SMEM_RAW_OFF + st * tm::RAW_BYTES + dst_lane;
@@ -296,10 +309,10 @@ encode_tm_kernel(const EncodeArgs a)
             const uint32_t ta0 = tmem_base + (uint32_t)tm::A_COL0;
             int it = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
-                const int acc = tl & 1;
-                const uint32_t acc_phase = (uint32_t)(tl >> 1) & 1u;
+                const int acc = WIDE ? 0 : (tl & 1);
+                const uint32_t acc_phase = (uint32_t)(tl / tm::ACC_STAGES) & 1u;
                 TM_WAIT(bar_tempty + 8 * acc, acc_phase ^ 1u, 5);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * tm::H);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * tm::HP);
 #pragma unroll 1
                 for (int kb = 0; kb < tm::NKB; ++kb, ++it) {
                     const int as = it & (tm::A_STAGES - 1), ws = it & 1;
@@ -311,7 +324,7 @@ encode_tm_kernel(const EncodeArgs a)
                         const uint32_t ta = ta0 + (uint32_t)(as * tm::A_STAGE_COLS);
 #pragma unroll
                         for (int k = 0; k < tm::KB / 16; ++k) {
-                            if (!FULL_E && (kb & 1) * tm::KB + k * 16 >= a.Et) break;       // k-steps of pure padding
+                            if (!FULL_E && (kb % tm::NQ) * tm::KB + k * 16 >= a.Et) break;  // k-steps of pure padding
                             const uint32_t a_hi = ta + k * 8, a_lo = ta + tm::KB / 2 + k * 8;
                             const uint64_t w_hi = w_hi0 + (uint64_t)(k * 2);                  // + 32 B
                             const uint64_t w_lo = w_hi + (uint64_t)(tm::TILE_BYTES >> 4);
@@ -365,32 +378,41 @@ encode_tm_kernel(const EncodeArgs a)
     }
 }
 
-int launch_encode_tm(const EncodeArgs &a, cudaStream_t st)
+template <bool WIDE>
+static int launch_tm(void (*kern)(const EncodeArgs), const EncodeArgs &a, cudaStream_t st)
 {
+    using C = TmCfg<WIDE>;
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const bool drop = a.drop_p > 0.0f, full = a.Et == tm::E;
-    void (*kern)(const EncodeArgs) = nullptr;
-    if (a.H == 128) {
-        kern = full ? (drop ? encode_tm_kernel<true, true, 128> : encode_tm_kernel<false, true, 128>)
-                    : (drop ? encode_tm_kernel<true, false, 128> : encode_tm_kernel<false, false, 128>);
-    } else if (a.H == 100) {
-        kern = full ? (drop ? encode_tm_kernel<true, true, 100> : encode_tm_kernel<false, true, 100>)
-                    : (drop ? encode_tm_kernel<true, false, 100> : encode_tm_kernel<false, false, 100>);
-    } else {
-        set_error("encode_tm_kernel: encode_size %d not supported (100 or 128)", a.H);
-        return C2V_EUNSUPPORTED;
-    }
     EncodeArgs b = a;
-    const char *dbg = getenv("C2V_DEBUG_FLAGS");      // timing experiments only (results become wrong)
+    const char *dbg = getenv("C2V_DEBUG_FLAGS");      // timing experiments (-DC2V_EXPERIMENTS builds only)
     if (dbg) b.flags |= atoi(dbg);
-    C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tm::SMEM_BYTES));
+    C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     int grid = a.n_tiles < sms ? a.n_tiles : sms;
     if (grid < 1) grid = 1;
-    C2V_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(tm::THREADS), (size_t)tm::SMEM_BYTES, st, b));
+    C2V_CUDA_OK(launch_pdl(kern, dim3((unsigned)grid), dim3(C::THREADS), (size_t)C::SMEM_BYTES, st, b));
     C2V_COUNT_LAUNCH();
     return C2V_OK;
+}
+
+int launch_encode_tm(const EncodeArgs &a, cudaStream_t st)
+{
+    const bool drop = a.drop_p > 0.0f;
+    if (a.H == 256) {
+        const bool full = a.Et == 256;
+        return launch_tm<true>(full ? (drop ? encode_tm_kernel<true, true, 256> : encode_tm_kernel<false, true, 256>)
+                                    : (drop ? encode_tm_kernel<true, false, 256> : encode_tm_kernel<false, false, 256>), a, st);
+    }
+    const bool full = a.Et == 128;
+    if (a.H == 128)
+        return launch_tm<false>(full ? (drop ? encode_tm_kernel<true, true, 128> : encode_tm_kernel<false, true, 128>)
+                                     : (drop ? encode_tm_kernel<true, false, 128> : encode_tm_kernel<false, false, 128>), a, st);
+    if (a.H == 100)
+        return launch_tm<false>(full ? (drop ? encode_tm_kernel<true, true, 100> : encode_tm_kernel<false, true, 100>)
+                                     : (drop ? encode_tm_kernel<true, false, 100> : encode_tm_kernel<false, false, 100>), a, st);
+    set_error("encode_tm_kernel: encode_size %d not supported (100, 128 or 256)", a.H);
+    return C2V_EUNSUPPORTED;
 }
 
 }  // namespace c2v

@@ -368,7 +368,7 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
 }
 
 // K (= encode_size) is zero-padded to a multiple of 64 inside the operand images
-bool label_tcgen05_shape_ok(const c2v_dims *d) { return d->encode >= 4 && d->encode <= 128 && (d->encode & 3) == 0; }
+bool label_tcgen05_shape_ok(const c2v_dims *d) { return d->encode >= 4 && d->encode <= 256 && (d->encode & 3) == 0; }
 
 static size_t lt_keys_bytes(int B) { return ((size_t)B * 8 + 1023) / 1024 * 1024; }
 
@@ -389,7 +389,7 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
                          cudaStream_t st)
 {
     if (!label_tcgen05_shape_ok(d)) {
-        set_error("tcgen05 label GEMM needs encode_size %% 4 == 0 and <= 128 (got %d)", d->encode);
+        set_error("tcgen05 label GEMM needs encode_size %% 4 == 0 and <= 256 (got %d)", d->encode);
         return C2V_EUNSUPPORTED;
     }
     const int H = d->encode, nkb = (H + 63) / 64;

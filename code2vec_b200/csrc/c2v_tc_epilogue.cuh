@@ -17,10 +17,11 @@ constexpr int XCH_BYTES = 4 * 4 * 3 * 32 * 4;      // [4 quarters][<=4 slices][3
 }  // namespace tce
 
 // LayerNorm affine pre-multiplied by 2*log2(e) so tanh needs no extra multiply; columns >= a.H (padding of the
-// 128-wide tile when encode_size < 128) get gamma' = beta' = attn = 0
+// HP-wide tile when encode_size < HP) get gamma' = beta' = attn = 0.  Layout: gamma'[HP] | beta'[HP] | attn[HP].
+template <int HP = tce::H>
 __device__ __forceinline__ void tce_fill_vectors(const EncodeArgs &a, float *s_vec, int tid) {
-    if (tid < 3 * tce::H) {
-        const int which = tid / tce::H, c = tid % tce::H;
+    if (tid < 3 * HP) {
+        const int which = tid / HP, c = tid % HP;
         float v = 0.0f;
         if (c < a.H) v = which == 0 ? a.ln_g[c] * tce::TWO_LOG2E : which == 1 ? a.ln_b[c] * tce::TWO_LOG2E : a.attn[c];
         s_vec[tid] = v;
@@ -183,6 +184,145 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
             tce_tile_body<DROPOUT, NS, HC>(a, s_vec, my_x, qx, x, q, hf, lane, vrow0, row, in_range, st_idx,
                                            inv_scale, 1.0f / (float)HV, vlast, n_valid);
         }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// encode_size 256 (BASELINE.json configs[3]): the accumulator is [128 rows x 256 columns] and there is only one of it
+// (TMEM: 256 accumulator + 256 A-stage columns), so the epilogue cannot keep a row in registers.  Warp (q, hf) owns rows
+// 32q.. and columns [128 hf, 128 hf + 128), walks them in 64-column chunks and goes over the accumulator four times:
+// sums -> mean | squared deviations -> variance | LayerNorm + tanh (+ dropout) + score, tanh output written BACK into
+// the accumulator (tcgen05.st) | softmax partials of the weighted sum from that output.  The MMAs of the next tile wait
+// for the last pass (bar_tempty), the loaders and converters keep running (4 A stages in TMEM).
+// ------------------------------------------------------------------------------------------------------------------
+template <bool DROPOUT>
+__device__ __forceinline__ void tce_epilogue_loop_wide(const EncodeArgs &a, float *s_vec, float *s_xch,
+                                                       uint32_t tmem_base, uint32_t bar_tfull, uint32_t bar_tempty,
+                                                       int warp, int lane, int my_tiles, long long *status)
+{
+    namespace tc = tce;
+    constexpr int HP = 256, NS = 2, HS = HP / NS, CH = 64, NCH = HS / CH;
+    const int q = warp & 3, hf = warp >> 2;
+    const float inv_scale = a.ws.prep_hdr[0];
+    const float inv_h = 1.0f / (float)HP;
+    float *my_x = s_xch + ((q * NS + hf) * 3) * 32 + lane;
+    const float *qx = s_xch + (q * NS * 3) * 32 + lane;
+    auto xsum = [&](int slot) {
+        float t = 0.0f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) t += qx[(s * 3 + slot) * 32];
+        return t;
+    };
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * HS);
+    auto load_chunk = [&](int ch, float (&x)[CH]) {
+        tmem_ld32(taddr + ch * CH, x);
+        tmem_ld32(taddr + ch * CH + 32, x + 32);
+        tmem_ld_wait();
+    };
+    for (int tl = 0; tl < my_tiles; ++tl) {
+        const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
+        const long long vrow0 = (long long)tile * tc::ROWS + q * tc::VROWS;
+        const long long row = vrow0 + lane;
+        const bool in_range = row < a.N;
+        const long long st_idx = in_range ? a.starts[row] : 0;       // model.py:64 mask = starts > 0
+        mbar_wait(bar_tfull, (uint32_t)tl & 1u, status);
+        tc_fence_after();
+        float x[CH];
+        // pass 1: mean (model.py:55-56)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            load_chunk(ch, x);
+#pragma unroll
+            for (int c = 0; c < CH; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
+        }
+        my_x[0] = (s0 + s1) + (s2 + s3);
+        named_bar_sync(1 + q, 32 * NS);
+        const float mean = xsum(0) * inv_h;
+        // pass 2: variance
+        s0 = s1 = s2 = s3 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            load_chunk(ch, x);
+#pragma unroll
+            for (int c = 0; c < CH; c += 4) {
+                const float d0 = x[c] - mean, d1 = x[c + 1] - mean, d2 = x[c + 2] - mean, d3 = x[c + 3] - mean;
+                s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+            }
+        }
+        my_x[32] = (s0 + s1) + (s2 + s3);
+        named_bar_sync(1 + q, 32 * NS);
+        const float var = xsum(1) * inv_h * inv_scale * inv_scale;
+        const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
+        const float shift = -mean * nrm;
+        // pass 3: tanh (model.py:57), dropout (:60-61), score h.a (:92-93); h goes back into the accumulator
+        float u0 = 0.f, u1 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            load_chunk(ch, x);
+            const float4 *sG = reinterpret_cast<const float4 *>(s_vec + hf * HS + ch * CH);
+            const float4 *sB = reinterpret_cast<const float4 *>(s_vec + HP + hf * HS + ch * CH);
+            const float4 *sA = reinterpret_cast<const float4 *>(s_vec + 2 * HP + hf * HS + ch * CH);
+#pragma unroll
+            for (int c4 = 0; c4 < CH / 4; ++c4) {
+                const float4 g = sG[c4], b = sB[c4], at = sA[c4];
+                float y0 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 0], nrm, shift), g.x, b.x));
+                float y1 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 1], nrm, shift), g.y, b.y));
+                float y2 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 2], nrm, shift), g.z, b.z));
+                float y3 = tanh_from_scaled(fmaf(fmaf(x[4 * c4 + 3], nrm, shift), g.w, b.w));
+                if (DROPOUT) {
+                    const uint4 bits = dropout_bits(a.seed, row, (hf * HS + ch * CH) / 4 + c4);
+                    y0 *= dropout_mul(bits.x, a.drop_p, a.drop_scale);
+                    y1 *= dropout_mul(bits.y, a.drop_p, a.drop_scale);
+                    y2 *= dropout_mul(bits.z, a.drop_p, a.drop_scale);
+                    y3 *= dropout_mul(bits.w, a.drop_p, a.drop_scale);
+                }
+                x[4 * c4 + 0] = y0; x[4 * c4 + 1] = y1; x[4 * c4 + 2] = y2; x[4 * c4 + 3] = y3;
+                u0 = fmaf(y0, at.x, u0); u1 = fmaf(y1, at.y, u1);
+                u0 = fmaf(y2, at.z, u0); u1 = fmaf(y3, at.w, u1);
+            }
+            tmem_st32(taddr + ch * CH, x);
+            tmem_st32(taddr + ch * CH + 32, x + 32);
+        }
+        tmem_st_wait_all();
+        my_x[64] = u0 + u1;
+        named_bar_sync(1 + q, 32 * NS);
+        const float u = xsum(2);
+        const float z = (in_range && st_idx > 0) ? u : C2V_NINF;     // model.py:93
+        if (hf == 0 && in_range) a.attention[row] = z;
+        // pass 4: per-(warp, bag) online-softmax partials of the weighted sum
+        if (vrow0 < a.N) {
+            const long long vt = vrow0 / tc::VROWS;
+            long long last = vrow0 + tc::VROWS - 1; if (last > a.N - 1) last = a.N - 1;
+            const long long bag_lo = vrow0 / a.L, bag_hi = last / a.L;
+            const long long my_bag = row / a.L;
+            for (long long bag = bag_lo; bag <= bag_hi; ++bag) {
+                const bool in_seg = in_range && my_bag == bag;
+                const float m = warp_max(in_seg ? z : -INFINITY);
+                const float e = in_seg ? __expf(z - m) : 0.0f;
+                const size_t slot = (size_t)(vt + bag);
+                float *pv = a.ws.part_v + slot * a.H + hf * HS;
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch) {
+                    load_chunk(ch, x);
+#pragma unroll
+                    for (int c = 0; c < CH / 32; ++c) {
+                        float t[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) t[j] = e * x[c * 32 + j];
+                        butterfly_reduce32(t, lane);
+                        pv[ch * CH + c * 32 + lane] = t[0];
+                    }
+                }
+                if (hf == 0) {
+                    const float ssum = warp_sum(e);
+                    if (lane == 0) { a.ws.part_m[slot] = m; a.ws.part_s[slot] = ssum; }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty);                     // the (only) accumulator is free again
+    }
 }
 
 }  // namespace c2v

@@ -52,10 +52,12 @@ def test_size_queries_and_argument_checks_without_a_gpu():
     d2 = _lib.Dims(1000, 800, 64, 100, 100, 100, 0)        # the reference's defaults (main.py:56-58)
     assert lib.c2v_encode_supports_tcgen05(ctypes.byref(d2)) == 1
     for bad in (_lib.Dims(1000, 800, 64, 100, 96, 100, 0),      # terminal_embed != path_embed
-                _lib.Dims(1000, 800, 64, 256, 256, 256, 0),     # > 128
+                _lib.Dims(1000, 800, 64, 256, 256, 128, 0),     # embed > 128 needs encode_size 256
+                _lib.Dims(1000, 800, 64, 260, 260, 256, 0),     # > 256
                 _lib.Dims(1000, 800, 64, 128, 128, 64, 0),      # encode_size not in {100, 128}
                 _lib.Dims(10_000_000, 800, 64, 128, 128, 128, 0)):   # table > 4 GB (32-bit row offsets)
         assert lib.c2v_encode_supports_tcgen05(ctypes.byref(bad)) == 0
+    assert lib.c2v_encode_supports_tcgen05(ctypes.byref(_lib.Dims(1000, 800, 64, 256, 256, 256, 0))) == 1   # BASELINE configs[3]
     # NULL pointers are rejected before any CUDA call
     rc = lib.c2v_encode_forward(ctypes.byref(d), None, None, None, None, 4, 7, None, None, None, None, 0, 0, None)
     assert rc == _lib.C2V_EINVAL

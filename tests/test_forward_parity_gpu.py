@@ -67,7 +67,8 @@ def test_forward_matches_oracle_on_seeded_inputs(algo, B, L):
     assert np.abs(out.cpu().numpy() - ref_out).max() <= EXPECT * 4
 
 
-@pytest.mark.parametrize("E,H", [(100, 100), (128, 100), (100, 128), (64, 128), (36, 100), (4, 100)])
+@pytest.mark.parametrize("E,H", [(100, 100), (128, 100), (100, 128), (64, 128), (36, 100), (4, 100),
+                                 (256, 256), (200, 256), (64, 256)])
 @pytest.mark.parametrize("B,L", [(3, 200), (37, 50), (130, 31)])
 def test_padded_shapes_on_the_tensor_core_path(E, H, B, L):
     """K1e pads every sub-vector to 128 k (zero-filled cp.async chunks) and the encode size to 128 columns
@@ -147,7 +148,7 @@ def test_out_of_range_index_is_reported_like_the_reference():
                               check_indices=True)
 
 
-@pytest.mark.parametrize("E,H", [(128, 128), (100, 100)])
+@pytest.mark.parametrize("E,H", [(128, 128), (100, 100), (256, 256)])
 @pytest.mark.parametrize("algo", ["ffma", "tcgen05"])
 def test_training_mode_dropout_matches_oracle_with_same_mask(algo, E, H):
     """model.py:60-61.  The kernel's mask is a pure function of (seed, row, col); the test rebuilds
@@ -234,7 +235,7 @@ def test_host_buffer_api_matches_device_api():
 
 
 @pytest.mark.parametrize("B,C,H", [(1, 5, 128), (37, 77, 128), (130, 1000, 128), (1024, 8192, 128), (64, 300, 64), (9, 50, 100),
-                                   (200, 2279, 100), (33, 70, 36), (5, 40, 130)])
+                                   (200, 2279, 100), (33, 70, 36), (5, 40, 130), (130, 1000, 256), (40, 300, 200)])
 def test_label_logits_tcgen05_vs_ffma_vs_oracle(B, C, H):
     """model.py:83 on the tensor cores (3-pass fp16 split) against the CUDA-core GEMM and the oracle,
     incl. ragged tile edges and weights at 'trained' scale."""
@@ -249,7 +250,7 @@ def test_label_logits_tcgen05_vs_ffma_vs_oracle(B, C, H):
     tol = 3e-6 * max(1.0, float(np.abs(ref).max()))      # fp32 relative: logits reach +-30 here
     out_f = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_FFMA).cpu().numpy()
     assert np.abs(out_f - ref).max() <= tol
-    if H % 4 == 0 and H <= 128:
+    if H % 4 == 0 and H <= 256:
         out_t = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_TCGEN05).cpu().numpy()
         assert np.abs(out_t - ref).max() <= tol, np.abs(out_t - ref).max()
         out_a = CF.label_logits(dims, params, cuda(cvn), algo=_lib.ALGO_AUTO).cpu().numpy()
