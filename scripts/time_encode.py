@@ -60,3 +60,14 @@ for spec in (sys.argv[1:] or ["tm"]):
         names = ["ld:rempty", "cv:rfull", "cv:aempty", "mma:afull", "mma:wfull", "mma:tempty", "w:wempty"]
         print("   wait cycles (CTA 0): " + "  ".join(f"{n}={st[4 + i]}" for i, n in enumerate(names)) + f"  total={st[15]}")
     print(f"{wl} {var} flags={fl or 0}: {us:.2f} us/launch  {alg_bytes / us / 1e3:.0f} GB/s  frac={alg_bytes / us / 1e3 / peak:.3f}  max|err vs ffma|={err:.2e}", flush=True)
+if os.environ.get("TIME_FFMA"):
+    for i in range(3):
+        CF.encode_forward(dims, params, s[:B], pth[:B], e[:B], algo=_lib.ALGO_FFMA, cache=cache, weight=p["input_linear.weight"])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(10):
+        o = (i % nb) * B
+        CF.encode_forward(dims, params, s[o:o + B], pth[o:o + B], e[o:o + B], algo=_lib.ALGO_FFMA)
+    e1.record(); torch.cuda.synchronize()
+    print(f"{wl} ffma (whole call): {e0.elapsed_time(e1) / 10 * 1e3:.1f} us", flush=True)
