@@ -346,3 +346,33 @@ def test_fused_argmax_at_top11_label_count():
     assert torch.equal(mx, tv) and torch.equal(am, ti)
     ref = cvt[:64].double() @ w.double().T + bias.double()
     assert (out[:64].double() - ref).abs().max().item() <= 3e-6 * max(1.0, ref.abs().max().item())
+
+
+def test_wide_configuration_full_shard_properties():
+    """BASELINE.json configs[3] per-GPU shard (512 x 200, embed = encode = 256) on the 256-wide tensor-core configuration
+    (one TMEM accumulator, 4-pass chunked epilogue): size-independent properties on all rows, the CUDA-core kernel on
+    all rows, the oracle on a sample of bags, and bit-identical relaunches."""
+    from oracle import oracle
+    rng = np.random.default_rng(21)
+    T, P, C, E, H, B, L = 30000, 20000, 64, 256, 256, 512, 200
+    p = random_params(rng, T, P, C, E, E, H)
+    starts, paths, ends, label = random_batch(rng, B, L, T, P, C, ragged=True)
+    starts[3, :] = 0
+    dims = CF.make_dims(T, P, C, E, E, H)
+    tp = {k: cuda(v) for k, v in p.items()}
+    params = CF.make_params(tp["terminal_embedding.weight"], tp["path_embedding.weight"], tp["input_linear.weight"],
+                            tp["input_layer_norm.weight"], tp["input_layer_norm.bias"], tp["attention_parameter"])
+    s, pp, e = cuda(starts), cuda(paths), cuda(ends)
+    cv, att = CF.encode_forward(dims, params, s, pp, e, algo=_lib.ALGO_TCGEN05, check_indices=True)
+    cv2, att2 = CF.encode_forward(dims, params, s, pp, e, algo=_lib.ALGO_TCGEN05)
+    assert torch.equal(cv, cv2) and torch.equal(att, att2)
+    a = att.cpu().numpy(); v = cv.cpu().numpy()
+    assert np.allclose(a.sum(1), 1.0, atol=2e-5) and (a >= 0).all() and np.abs(v).max() <= 1.0 + 1e-6
+    assert np.allclose(a[3], 1.0 / L, atol=1e-7)                 # all-pad bag: uniform attention (model.py:93-96)
+    cvf, attf = CF.encode_forward(dims, params, s, pp, e, algo=_lib.ALGO_FFMA)
+    assert np.abs(cvf.cpu().numpy() - v).max() <= EXPECT and np.abs(attf.cpu().numpy() - a).max() <= EXPECT
+    sel = rng.choice(B, 6, replace=False)
+    ref_cv, ref_att = oracle.encode_forward(starts[sel], paths[sel], ends[sel], p["terminal_embedding.weight"],
+                                            p["path_embedding.weight"], p["input_linear.weight"],
+                                            p["input_layer_norm.weight"], p["input_layer_norm.bias"], p["attention_parameter"])
+    assert np.abs(v[sel] - ref_cv).max() <= EXPECT and np.abs(a[sel] - ref_att).max() <= EXPECT
