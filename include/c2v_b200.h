@@ -211,6 +211,18 @@ int c2v_forward_host_async(c2v_session *s, const c2v_params *p,
                            int64_t *pred_label, float *pred_score, int32_t algo, int64_t *ticket);
 int c2v_session_wait(c2v_session *s, int64_t ticket);
 
+/* On-GPU batch construction for the method-name task: replaces DatasetBuilder.build_data
+ * (model/dataset_builder.py:112-150, infer_method branch).  The corpus stays on the device as CSR:
+ * offsets [n_items + 1] (int64), contexts [offsets[n_items]][3] (int32: start, path, end), item_labels [n_items]
+ * (int64, may be NULL).  Row b of starts / paths / ends [B, L] (int64, device) receives a uniformly random subset of
+ * min(n, L) contexts of method item_ids[b] -- the reference shuffles and truncates -- with @method_0 rewritten to
+ * @question (:136-143) and a zero-padded suffix (:212-219); label[b] = item_labels[item_ids[b]] (label may be NULL).
+ * The choice is a pure function of (seed, item, context index); an item id outside [0, n_items) yields an all-pad row. */
+int c2v_build_batch(const int64_t *offsets, const int32_t *contexts, int64_t n_items,
+                    const int64_t *item_ids, const int64_t *item_labels, int32_t B, int32_t L,
+                    uint64_t seed, int64_t method_token, int64_t question_token, int64_t *starts,
+                    int64_t *paths, int64_t *ends, int64_t *label, void *stream);
+
 /* Counts kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t c2v_launch_count(void);
 

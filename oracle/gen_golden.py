@@ -169,6 +169,40 @@ def real_batch():
     dump("real_batch", o2, small, tmap[starts], pmap[paths], tmap[ends], lmap[label])
 
 
+def builder_corpus():
+    """The reference's own reader + builder on dataset/corpus.txt (dataset_reader.py:44-128, dataset_builder.py:112-150):
+    the contexts of 64 methods (all the long ones first, so that n > max_path_length is covered) as CSR, and what
+    `DatasetBuilder.build_data` made of them under random.seed(11) -- the pin of oracle/batch_oracle.py."""
+    import random
+    import logging
+    import numpy as np
+    logging.disable(logging.CRITICAL)
+    from model.dataset_builder import DatasetBuilder
+    from model.dataset_reader import DatasetReader
+    random.seed(11)
+    reader = DatasetReader(f"{REF}/dataset/corpus.txt", f"{REF}/dataset/path_idxs.txt",
+                           f"{REF}/dataset/terminal_idxs.txt", infer_method=True, infer_variable=False,
+                           shuffle_variable_indexes=False)
+    o = option(reader.terminal_vocab.len(), reader.path_vocab.len(), reader.label_vocab.len(), 100, 100, 100)
+    o.max_path_length, o.eval_method, o.batch_size = 200, "exact", 32
+    builder = DatasetBuilder(reader, o)
+    items = sorted(reader.items, key=lambda it: -len(it.path_contexts))
+    items = items[:6] + [it for it in items if 150 <= len(it.path_contexts) <= 260][:10] + items[len(items) // 2:len(items) // 2 + 40] + items[-8:]
+    offsets = np.zeros(len(items) + 1, dtype=np.int64)
+    ctx = []
+    for i, it in enumerate(items):
+        offsets[i + 1] = offsets[i] + len(it.path_contexts)
+        ctx.extend(it.path_contexts)                       # stored order BEFORE build_data shuffles in place
+    ctx = np.asarray(ctx, dtype=np.int32).reshape(-1, 3)
+    ids, starts, paths, ends, label = builder.build_data(reader, items, o.max_path_length)
+    np.savez_compressed(os.path.join(OUT, "builder_corpus.npz"), offsets=offsets, contexts=ctx,
+                        method_token=np.int64(reader.terminal_vocab.stoi["@method_0"]),
+                        question_token=np.int64(reader.QUESTION_TOKEN_INDEX), max_path_length=np.int64(o.max_path_length),
+                        ref_starts=starts.numpy(), ref_paths=paths.numpy(), ref_ends=ends.numpy(), ref_label=label.numpy(),
+                        item_label=np.asarray([reader.label_vocab.stoi[it.normalized_label] for it in items], dtype=np.int64))
+    print("builder_corpus:", len(items), "items,", len(ctx), "contexts, longest", int(np.diff(offsets).max()))
+
+
 def init_fingerprint():
     """Initial weights under torch.manual_seed (main.py:120): the boundary module must
     create its parameters in the same RNG order."""
@@ -201,3 +235,4 @@ if __name__ == "__main__":
     seeded("grad_cfg1", 14, 3, 40, 120, 90, 12, 100, 100, 100, grads=True, allpad_rows=(1,))
     init_fingerprint()
     real_batch()
+    builder_corpus()
