@@ -18,6 +18,7 @@
 //   backward_rows_kernel : recompute + dx (kept in smem and written to a [N,H] buffer) +
 //                          da/dgamma/dbeta + dC = dX.W scattered with 128-bit vector atomics
 //   backward_dw_kernel   : dW = dX^T . C  (split over context rows, gathered C operand)
+#include <cstdlib>
 #include <cstring>
 
 #include "c2v_ffma_tile.cuh"
@@ -25,6 +26,8 @@
 namespace c2v {
 
 int launch_transpose_w(const float *W, float *Wt, int H, int D, int Hs, cudaStream_t st);
+bool backward_dw_tc_ok(const EncodeArgs &a);
+int launch_backward_dw_tc(const EncodeArgs &a, const float *dx, float *dW, cudaStream_t st);
 
 struct BackwardArgs {
     const float *cv, *att, *d_cv, *d_att, *sb;   // sb[b] = sum_j att[b,j] d_att[b,j] (or null)
@@ -392,6 +395,10 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     kern<<<grid, THREADS, smem, st>>>(a, b, Hs);
     C2V_LAUNCH_OK("backward_rows_kernel");
 
+    // dW = dX^T . C: tensor cores when the shape allows (c2v_backward_dw_tc.cu), C2V_BACKWARD_DW=ffma forces the CUDA cores
+    const char *dw_env = getenv("C2V_BACKWARD_DW");
+    if (backward_dw_tc_ok(a) && !(dw_env && !strcmp(dw_env, "ffma")))
+        return launch_backward_dw_tc(a, dx, g->input_linear, st);
     const int gx = (a.D + DW_T - 1) / DW_T, gy = (a.H + DW_T - 1) / DW_T;
     long long split = (8LL * sms) / (gx * gy);
     if (split < 1) split = 1;
