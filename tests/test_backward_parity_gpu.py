@@ -115,3 +115,36 @@ def test_one_adam_step_matches_reference_training_semantics():
         # where the gradient is ~0 and tightly elsewhere
         d = np.abs(sd[k].cpu().numpy() - tp[k].detach().numpy())
         assert np.quantile(d, 0.999) <= 2e-4, k
+
+
+def test_tensor_core_dw_matches_the_cuda_core_gemm_at_many_tiles_per_cta():
+    """K3b (dW = dX^T . C on tcgen05, MN-major operands) against the CUDA-core kernel on 51,200 context rows = 400
+    tiles (every CTA walks several tiles: operand stage / ring reuse and the TMEM-resident partial), ragged bags and an
+    all-pad bag included; and against the fp64 product of the same dX on a slice of rows."""
+    import os
+    rng = np.random.default_rng(13)
+    T, P, C, E, H, B, L = 3000, 2000, 16, 128, 128, 256, 200
+    p = random_params(rng, T, P, C, E, E, H)
+    starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
+    starts[7, :] = 0
+    dims = CF.make_dims(T, P, C, E, E, H)
+    tp = {k: cuda(v) for k, v in p.items()}
+    params = CF.make_params(tp["terminal_embedding.weight"], tp["path_embedding.weight"], tp["input_linear.weight"],
+                            tp["input_layer_norm.weight"], tp["input_layer_norm.bias"], tp["attention_parameter"],
+                            tp["output_linear.weight"], tp["output_linear.bias"])
+    s, pp, e = cuda(starts), cuda(paths), cuda(ends)
+    cv, att = CF.encode_forward(dims, params, s, pp, e)
+    d_cv = cuda(rng.standard_normal((B, H)).astype(np.float32))
+    shapes = {"terminal_embedding": (T, E), "path_embedding": (P, E), "input_linear": (H, 3 * E), "ln_weight": (H,),
+              "ln_bias": (H,), "attention": (H,)}
+    os.environ["C2V_BACKWARD_DW"] = "ffma"
+    try:
+        g_ffma = CF.encode_backward(dims, params, s, pp, e, cv, att, d_cv, None, shapes)
+    finally:
+        del os.environ["C2V_BACKWARD_DW"]
+    g_tc = CF.encode_backward(dims, params, s, pp, e, cv, att, d_cv, None, shapes)
+    a, b = g_tc["input_linear"].cpu().numpy(), g_ffma["input_linear"].cpu().numpy()
+    assert np.abs(b).max() > 1.0
+    assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
+    for k in ("terminal_embedding", "path_embedding", "ln_weight", "ln_bias", "attention"):
+        assert torch.allclose(g_tc[k], g_ffma[k], rtol=0, atol=2e-5 * float(g_ffma[k].abs().max()))
