@@ -51,6 +51,8 @@ SYMBOLS = {
     "c2v_encode_workspace_bytes": (c_sz, [_P(Dims), c_i32, c_i32]),
     "c2v_encode_forward": (ctypes.c_int, [_P(Dims), _P(Params), c_vp, c_vp, c_vp, c_i32, c_i32, _P(Dropout),
                                           c_vp, c_vp, c_vp, c_sz, c_i32, c_vp]),
+    "c2v_encode_forward_stash": (ctypes.c_int, [_P(Dims), _P(Params), c_vp, c_vp, c_vp, c_i32, c_i32, _P(Dropout),
+                                                c_vp, c_vp, c_vp, c_vp, c_sz, c_i32, c_vp]),
     "c2v_workspace_status": (c_i64, [c_vp, c_vp]),
     "c2v_label_workspace_bytes": (c_sz, [_P(Dims), c_i32]),
     "c2v_label_logits": (ctypes.c_int, [_P(Dims), _P(Params), c_vp, c_i32, c_vp, c_vp, c_sz, c_i32, c_vp]),
@@ -64,6 +66,8 @@ SYMBOLS = {
     "c2v_encode_backward_workspace_bytes": (c_sz, [_P(Dims), c_i32, c_i32]),
     "c2v_encode_backward": (ctypes.c_int, [_P(Dims), _P(Params), c_vp, c_vp, c_vp, c_i32, c_i32, _P(Dropout),
                                            c_vp, c_vp, c_vp, c_vp, _P(Grads), c_vp, c_sz, c_vp]),
+    "c2v_encode_backward_stashed": (ctypes.c_int, [_P(Dims), _P(Params), c_vp, c_vp, c_vp, c_i32, c_i32, _P(Dropout),
+                                                   c_vp, c_vp, c_vp, c_vp, c_vp, _P(Grads), c_vp, c_sz, c_vp]),
     "c2v_session_create": (ctypes.c_int, [ctypes.c_int, _P(Dims), c_i32, c_i32, _P(c_vp)]),
     "c2v_session_destroy": (None, [c_vp]),
     "c2v_forward_host": (ctypes.c_int, [c_vp, _P(Params), c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp,

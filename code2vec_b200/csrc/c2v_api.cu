@@ -37,7 +37,7 @@ int launch_colsum(const float *X, int B, long long C, float *out, cudaStream_t s
 int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeArgs &a, int B,
                            const float *cv, const float *attention, const float *d_cv,
                            const float *d_att, const c2v_grads *g, void *ws, size_t ws_bytes,
-                           cudaStream_t st);
+                           cudaStream_t st, const float *x_stash);
 size_t encode_backward_workspace_bytes(const c2v_dims *d, int B, int L);
 bool label_tcgen05_shape_ok(const c2v_dims *d);
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B);
@@ -150,6 +150,15 @@ int c2v_encode_forward(const c2v_dims *d, const c2v_params *p, const int64_t *st
                        const c2v_dropout *drop, float *code_vector, float *attention,
                        void *workspace, size_t workspace_bytes, int32_t algo, void *stream)
 {
+    return c2v_encode_forward_stash(d, p, starts, paths, ends, B, L, drop, code_vector, attention, nullptr, workspace,
+                                    workspace_bytes, algo, stream);
+}
+
+int c2v_encode_forward_stash(const c2v_dims *d, const c2v_params *p, const int64_t *starts,
+                             const int64_t *paths, const int64_t *ends, int32_t B, int32_t L,
+                             const c2v_dropout *drop, float *code_vector, float *attention, float *x_stash,
+                             void *workspace, size_t workspace_bytes, int32_t algo, void *stream)
+{
     if (!dims_ok(d)) return C2V_EINVAL;
     if (!p || !starts || !paths || !ends || !code_vector || !attention || !workspace) {
         set_error("c2v_encode_forward: NULL pointer argument");
@@ -202,6 +211,7 @@ int c2v_encode_forward(const c2v_dims *d, const c2v_params *p, const int64_t *st
         a.drop_p = drop->p; a.drop_scale = 1.0f / (1.0f - drop->p); a.seed = drop->seed;
     }
     a.attention = attention;
+    a.stash_x = x_stash;
     a.flags = 0;
     // rows per softmax partial: 64-row CTA tiles (FFMA) or 32-row epilogue warps (tcgen05)
     ws.tile_rows = use_tc ? 32 : 64;
@@ -390,6 +400,16 @@ int c2v_encode_backward(const c2v_dims *d, const c2v_params *p, const int64_t *s
                         const float *d_code_vector, const float *d_attention, const c2v_grads *grads,
                         void *workspace, size_t workspace_bytes, void *stream)
 {
+    return c2v_encode_backward_stashed(d, p, starts, paths, ends, B, L, drop, code_vector, attention, nullptr,
+                                       d_code_vector, d_attention, grads, workspace, workspace_bytes, stream);
+}
+
+int c2v_encode_backward_stashed(const c2v_dims *d, const c2v_params *p, const int64_t *starts,
+                                const int64_t *paths, const int64_t *ends, int32_t B, int32_t L,
+                                const c2v_dropout *drop, const float *code_vector, const float *attention,
+                                const float *x_stash, const float *d_code_vector, const float *d_attention,
+                                const c2v_grads *grads, void *workspace, size_t workspace_bytes, void *stream)
+{
     if (!dims_ok(d)) return C2V_EINVAL;
     if (!p || !starts || !paths || !ends || !code_vector || !attention || !d_code_vector || !grads ||
         !workspace || B < 1 || L < 1) {
@@ -418,7 +438,7 @@ int c2v_encode_backward(const c2v_dims *d, const c2v_params *p, const int64_t *s
     }
     return launch_encode_backward(d, p, a, B, code_vector, attention, d_code_vector, d_attention,
                                   grads, workspace, workspace_bytes,
-                                  static_cast<cudaStream_t>(stream));
+                                  static_cast<cudaStream_t>(stream), x_stash);
 }
 
 }  // extern "C"

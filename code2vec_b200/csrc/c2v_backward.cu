@@ -31,6 +31,7 @@ int launch_backward_dw_tc(const EncodeArgs &a, const float *dx, float *dW, cudaS
 
 struct BackwardArgs {
     const float *cv, *att, *d_cv, *d_att, *sb;   // sb[b] = sum_j att[b,j] d_att[b,j] (or null)
+    const float *x_stash;                        // [N, H] x = c . W^T kept by the training forward (or null: recompute)
     const float *W;                              // [H, D] row-major (B operand of dC = dX . W)
     float *dx;                                   // [N, H]
     float *g_emb_t, *g_emb_p, *g_attn, *g_ln_g, *g_ln_b;
@@ -93,7 +94,15 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
         const long long row0 = (long long)tile * TM;
         tile_load_indices(a, row0, sidx);
         __syncthreads();
-        tile_gemm_xw<VEC>(a, sidx, Ac, Wc, X, Hs);             // recompute x = c . W^T
+        if (b.x_stash) {                                       // x kept by the forward: one coalesced tile load
+            for (int i = tid; i < TM * H; i += THREADS) {
+                const int r = i / H, c = i % H;
+                X[r * Hs + c] = row0 + r < a.N ? b.x_stash[(size_t)(row0 + r) * H + c] : 0.0f;
+            }
+            __syncthreads();
+        } else {
+            tile_gemm_xw<VEC>(a, sidx, Ac, Wc, X, Hs);         // recompute x = c . W^T
+        }
 
         // ---- per row: forward recompute of LN / tanh / dropout, then dx (one warp per row)
         for (int r = warp; r < TM; r += THREADS / 32) {
@@ -338,7 +347,7 @@ size_t encode_backward_workspace_bytes(const c2v_dims *d, int B, int L)
 
 int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeArgs &a_in, int B,
                            const float *cv, const float *attention, const float *d_cv, const float *d_att,
-                           const c2v_grads *g, void *ws, size_t ws_bytes, cudaStream_t st)
+                           const c2v_grads *g, void *ws, size_t ws_bytes, cudaStream_t st, const float *x_stash)
 {
     EncodeArgs a = a_in;
     if (a.H > 32 * MAXC) {
@@ -363,7 +372,7 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     int rc = launch_transpose_w(p->input_linear, w_t, a.H, a.D, Hs, st);
     if (rc != C2V_OK) return rc;
     BackwardArgs b;
-    b.cv = cv; b.att = attention; b.d_cv = d_cv; b.d_att = d_att; b.sb = nullptr;
+    b.cv = cv; b.att = attention; b.d_cv = d_cv; b.d_att = d_att; b.sb = nullptr; b.x_stash = x_stash;
     b.W = p->input_linear; b.dx = dx;
     b.g_emb_t = g->terminal_embedding; b.g_emb_p = g->path_embedding;
     b.g_attn = g->attention; b.g_ln_g = g->ln_weight; b.g_ln_b = g->ln_bias;

@@ -95,6 +95,7 @@ struct EncodeArgs {
     float drop_scale;       // 1/(1-p)
     unsigned long long seed;
     float *attention;       // [N] raw masked scores z (finalize turns them into softmax weights)
+    float *stash_x;         // optional [N, H]: x = c . W^T (model.py:54) of every row, kept for the backward
     int flags;              // debug switches (bit 0: producer-side proxy fence in the tcgen05 kernel)
     EncodeWorkspace ws;
 };

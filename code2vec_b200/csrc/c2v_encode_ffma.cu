@@ -65,6 +65,12 @@ encode_ffma_kernel(const EncodeArgs a, const int Hs)
         tile_load_indices(a, row0, sidx);                    // model.py:48-50
         __syncthreads();
         tile_gemm_xw<VEC>(a, sidx, Ac, Wc, X, Hs);           // x = c . W^T (model.py:51-54)
+        if (a.stash_x) {                                     // training forward: keep x for the backward
+            for (int i = threadIdx.x; i < TM * a.H; i += THREADS) {
+                const int r = i / a.H, c = i % a.H;
+                if (row0 + r < a.N) a.stash_x[(size_t)(row0 + r) * a.H + c] = X[r * Hs + c];
+            }
+        }
 
         // ---- LayerNorm + tanh (+dropout) + score, one warp per row (model.py:55-61, 92-93)
         for (int r = warp; r < TM; r += THREADS / 32) {

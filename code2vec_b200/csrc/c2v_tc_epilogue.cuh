@@ -180,6 +180,12 @@ __device__ __forceinline__ void tce_epilogue_loop(const EncodeArgs &a, float *s_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);           // accumulator is free again
             if (C2V_EXPT(a.flags, 16)) continue;        // timing experiment: producer side alone (results are wrong)
+            if (a.stash_x && in_range) {       // training forward: keep x = c . W^T for the backward (no recompute)
+                float4 *dst = reinterpret_cast<float4 *>(a.stash_x + (size_t)row * a.H + hf * HC);
+#pragma unroll
+                for (int c = 0; c < HC; c += 4)
+                    if (c < n_valid) dst[c / 4] = make_float4(x[c] * inv_scale, x[c + 1] * inv_scale, x[c + 2] * inv_scale, x[c + 3] * inv_scale);
+            }
 
             tce_tile_body<DROPOUT, NS, HC>(a, s_vec, my_x, qx, x, q, hf, lane, vrow0, row, in_range, st_idx,
                                            inv_scale, 1.0f / (float)HV, vlast, n_valid);
@@ -232,6 +238,12 @@ __device__ __forceinline__ void tce_epilogue_loop_wide(const EncodeArgs &a, floa
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ++ch) {
             load_chunk(ch, x);
+            if (a.stash_x && in_range) {
+                float4 *dst = reinterpret_cast<float4 *>(a.stash_x + (size_t)row * a.H + hf * HS + ch * CH);
+#pragma unroll
+                for (int c = 0; c < CH; c += 4)
+                    dst[c / 4] = make_float4(x[c] * inv_scale, x[c + 1] * inv_scale, x[c + 2] * inv_scale, x[c + 3] * inv_scale);
+            }
 #pragma unroll
             for (int c = 0; c < CH; c += 4) { s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3]; }
         }

@@ -66,8 +66,10 @@ class PrepCache:
 
 
 def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False, seed=0, algo=_lib.ALGO_AUTO,
-                   check_indices=False, cache=None, weight=None):
-    """-> (code_vector [B,H], attention [B,L]); model.py:48-69 + 90-96."""
+                   check_indices=False, cache=None, weight=None, stash=False):
+    """-> (code_vector [B,H], attention [B,L]); model.py:48-69 + 90-96.
+    stash=True (training): also returns x = c . W^T [B*L, H] for encode_backward(x_stash=...), which then skips the
+    re-gather and the recompute GEMM."""
     lib = _lib.load()
     _need_cuda(starts, paths, ends)
     B, L = starts.shape
@@ -84,9 +86,10 @@ def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False
         else:
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         drop = Dropout(float(drop_p), 1 if training else 0, int(seed))
-        rc = lib.c2v_encode_forward(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
-                                    B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(ws), ws.numel(), int(algo),
-                                    _stream(dev))
+        xs = torch.empty((B * L, dims.encode), dtype=torch.float32, device=dev) if stash else None
+        rc = lib.c2v_encode_forward_stash(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
+                                          B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(xs), _ptr(ws), ws.numel(),
+                                          int(algo), _stream(dev))
         _lib.check(rc, "c2v_encode_forward")
         if check_indices:
             bad = lib.c2v_workspace_status(_ptr(ws), _stream(dev))
@@ -94,6 +97,8 @@ def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False
                 raise IndexError("index out of range in self")
             if bad < 0:
                 _lib.check(int(bad), "c2v_workspace_status")
+    if stash:
+        return cv, att, xs
     return cv, att
 
 
@@ -191,8 +196,9 @@ def label_backward(dims, params, cv, d_out, need_cv=True, need_w=True, need_b=Tr
 
 
 def encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p=0.0, training=False,
-                    seed=0, grads_out=None):
-    """Gradients of the six encode parameters; returns dict name -> tensor."""
+                    seed=0, grads_out=None, x_stash=None):
+    """Gradients of the six encode parameters; returns dict name -> tensor.  x_stash: what encode_forward(stash=True)
+    returned for this batch (skips the re-gather + recompute GEMM)."""
     lib = _lib.load()
     B, L = starts.shape
     dev = starts.device
@@ -203,9 +209,10 @@ def encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, sha
         nbytes = lib.c2v_encode_backward_workspace_bytes(ctypes.byref(dims), B, L)
         ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
         drop = Dropout(float(drop_p), 1 if training else 0, int(seed))
-        rc = lib.c2v_encode_backward(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
-                                     B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(d_cv.contiguous()),
-                                     _ptr(d_att.contiguous()) if d_att is not None else None, ctypes.byref(grads),
-                                     _ptr(ws), nbytes, _stream(dev))
+        rc = lib.c2v_encode_backward_stashed(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
+                                             B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(x_stash),
+                                             _ptr(d_cv.contiguous()),
+                                             _ptr(d_att.contiguous()) if d_att is not None else None, ctypes.byref(grads),
+                                             _ptr(ws), nbytes, _stream(dev))
         _lib.check(rc, "c2v_encode_backward")
     return g

@@ -15,6 +15,8 @@ There is no CPU path: parameters and inputs must live on a CUDA (B200) device.
 """
 import math
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -34,8 +36,13 @@ class _EncodeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, dims, drop_p, training, seed, algo, cache):
         params = CF.make_params(emb_t, emb_p, W, ln_g, ln_b, attn)
-        cv, att = CF.encode_forward(dims, params, starts, paths, ends, drop_p, training, seed, algo,
-                                    cache=cache, weight=W)
+        # when a gradient will be asked for, keep x = c . W^T (105 MB per 1024 x 200 batch at encode_size 128) so that
+        # the backward neither re-gathers the embedding rows nor redoes the input_linear GEMM
+        stash = any(ctx.needs_input_grad[:6]) and os.environ.get("C2V_NO_STASH", "0") != "1"
+        res = CF.encode_forward(dims, params, starts, paths, ends, drop_p, training, seed, algo,
+                                cache=cache, weight=W, stash=stash)
+        cv, att = res[0], res[1]
+        ctx.x_stash = res[2] if stash else None
         ctx.save_for_backward(emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, cv, att)
         ctx.cfg = (dims, drop_p, training, seed)
         return cv, att
@@ -49,7 +56,9 @@ class _EncodeFn(torch.autograd.Function):
                   "ln_weight": ln_g.shape, "ln_bias": ln_b.shape, "attention": attn.shape}
         if d_cv is None:
             d_cv = torch.zeros_like(cv)
-        g = CF.encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p, training, seed)
+        g = CF.encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p, training, seed,
+                               x_stash=ctx.x_stash)
+        ctx.x_stash = None
         return (g["terminal_embedding"], g["path_embedding"], g["input_linear"], g["ln_weight"], g["ln_bias"],
                 g["attention"], None, None, None, None, None, None, None, None, None)
 

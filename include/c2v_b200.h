@@ -135,6 +135,12 @@ int c2v_encode_forward(const c2v_dims *d, const c2v_params *p,
                        int32_t B, int32_t L, const c2v_dropout *drop,
                        float *code_vector, float *attention,
                        void *workspace, size_t workspace_bytes, int32_t algo, void *stream);
+/* Training forward: additionally keeps the input_linear output x = c . W^T (model.py:54, before LayerNorm) of every
+ * context row in x_stash [B*L, H] (fp32, device) for c2v_encode_backward_stashed; x_stash == NULL: c2v_encode_forward. */
+int c2v_encode_forward_stash(const c2v_dims *d, const c2v_params *p, const int64_t *starts,
+                             const int64_t *paths, const int64_t *ends, int32_t B, int32_t L,
+                             const c2v_dropout *drop, float *code_vector, float *attention, float *x_stash,
+                             void *workspace, size_t workspace_bytes, int32_t algo, void *stream);
 
 /* Reads the status word of the last encode on this workspace (synchronises the
  * stream): returns the number of out-of-range indices seen, or a negative code. */
@@ -184,6 +190,14 @@ int c2v_encode_backward(const c2v_dims *d, const c2v_params *p,
                         const float *d_code_vector, const float *d_attention,
                         const c2v_grads *grads, void *workspace, size_t workspace_bytes,
                         void *stream);
+/* The same with x = c . W^T (model.py:54) of every context row read from x_stash [B*L, H] -- written by
+ * c2v_encode_forward_stash for the same batch -- instead of re-gathering the rows and redoing the GEMM
+ * (x_stash == NULL: identical to c2v_encode_backward). */
+int c2v_encode_backward_stashed(const c2v_dims *d, const c2v_params *p, const int64_t *starts,
+                                const int64_t *paths, const int64_t *ends, int32_t B, int32_t L,
+                                const c2v_dropout *drop, const float *code_vector, const float *attention,
+                                const float *x_stash, const float *d_code_vector, const float *d_attention,
+                                const c2v_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- host-buffer call: what a reference-side caller with CPU tensors uses ----------
  * One whole Code2Vec.forward + torch.max for a batch held in HOST memory (pinned

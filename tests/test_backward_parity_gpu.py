@@ -148,3 +148,35 @@ def test_tensor_core_dw_matches_the_cuda_core_gemm_at_many_tiles_per_cta():
     assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
     for k in ("terminal_embedding", "path_embedding", "ln_weight", "ln_bias", "attention"):
         assert torch.allclose(g_tc[k], g_ffma[k], rtol=0, atol=2e-5 * float(g_ffma[k].abs().max()))
+
+
+@pytest.mark.parametrize("E,H,algo", [(128, 128, "tcgen05"), (100, 100, "tcgen05"), (256, 256, "tcgen05"), (128, 128, "ffma"), (36, 52, "ffma")])
+def test_stashed_x_equals_the_input_linear_output_and_gives_the_same_gradients(E, H, algo):
+    """c2v_encode_forward_stash keeps x = c . W^T (model.py:54) per context row; c2v_encode_backward_stashed must give
+    the gradients of the recomputing backward (same kernels after x)."""
+    from gpu_util import ALGOS
+    rng = np.random.default_rng(E + H)
+    T, P, C, B, L = 400, 300, 9, 11, 77
+    p = random_params(rng, T, P, C, E, E, H)
+    starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
+    starts[2, :] = 0
+    dims = CF.make_dims(T, P, C, E, E, H)
+    tp = {k: cuda(v) for k, v in p.items()}
+    params = CF.make_params(tp["terminal_embedding.weight"], tp["path_embedding.weight"], tp["input_linear.weight"],
+                            tp["input_layer_norm.weight"], tp["input_layer_norm.bias"], tp["attention_parameter"])
+    s, pp, e = cuda(starts), cuda(paths), cuda(ends)
+    cv, att, xs = CF.encode_forward(dims, params, s, pp, e, drop_p=0.25, training=True, seed=5, algo=ALGOS[algo], stash=True)
+    c = np.concatenate([p["terminal_embedding.weight"][starts], p["path_embedding.weight"][paths],
+                        p["terminal_embedding.weight"][ends]], axis=2).reshape(B * L, 3 * E).astype(np.float64)
+    x_ref = c @ p["input_linear.weight"].astype(np.float64).T
+    err = float(np.abs(xs.cpu().numpy() - x_ref).max())
+    assert err <= 1e-5 * max(1.0, np.abs(x_ref).max()), err          # fp32 accumulation over K = 3E products (<= 768)
+    d_cv = cuda(rng.standard_normal((B, H)).astype(np.float32))
+    d_att = cuda(rng.standard_normal((B, L)).astype(np.float32))
+    shapes = {"terminal_embedding": (T, E), "path_embedding": (P, E), "input_linear": (H, 3 * E), "ln_weight": (H,),
+              "ln_bias": (H,), "attention": (H,)}
+    g0 = CF.encode_backward(dims, params, s, pp, e, cv, att, d_cv, d_att, shapes, drop_p=0.25, training=True, seed=5)
+    g1 = CF.encode_backward(dims, params, s, pp, e, cv, att, d_cv, d_att, shapes, drop_p=0.25, training=True, seed=5, x_stash=xs)
+    for k in shapes:
+        ref = g0[k].cpu().numpy()
+        assert np.abs(g1[k].cpu().numpy() - ref).max() <= _tol(ref), k
