@@ -27,11 +27,12 @@ namespace c2v {
 
 int launch_transpose_w(const float *W, float *Wt, int H, int D, int Hs, cudaStream_t st);
 bool backward_dw_tc_ok(const EncodeArgs &a);
-int launch_backward_dw_tc(const EncodeArgs &a, const float *dx, float *dW, cudaStream_t st);
+int launch_backward_dw_tc(const EncodeArgs &a, const float *dx, const unsigned *dx_absmax, float *dW, cudaStream_t st);
 
 struct BackwardArgs {
     const float *cv, *att, *d_cv, *d_att, *sb;   // sb[b] = sum_j att[b,j] d_att[b,j] (or null)
     const float *x_stash;                        // [N, H] x = c . W^T kept by the training forward (or null: recompute)
+    unsigned *dx_absmax;                         // bits of max |dx| over the batch (atomicMax; for the fp16 split of K3b)
     const float *W;                              // [H, D] row-major (B operand of dC = dX . W)
     float *dx;                                   // [N, H]
     float *g_emb_t, *g_emb_p, *g_attn, *g_ln_g, *g_ln_b;
@@ -87,6 +88,7 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
     const float invH = 1.0f / (float)H;
 
     float acc_a[MAXC], acc_g[MAXC], acc_b[MAXC];              // per-lane partial da / dgamma / dbeta
+    float dx_max = 0.0f;
 #pragma unroll
     for (int k = 0; k < MAXC; ++k) acc_a[k] = acc_g[k] = acc_b[k] = 0.0f;
 
@@ -166,6 +168,7 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
                     const float dxv = rstd * (dxh[k] - m1 - xh[k] * m2);
                     xr[c] = dxv;
                     b.dx[row * H + c] = dxv;
+                    dx_max = fmaxf(dx_max, fabsf(dxv));
                 }
             }
             for (int c = H + lane; c < Hs; c += 32) xr[c] = 0.0f;
@@ -250,6 +253,8 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
         __syncthreads();
     }
 
+    dx_max = warp_max(dx_max);
+    if (lane == 0 && dx_max > 0.0f) atomicMax(b.dx_absmax, __float_as_uint(dx_max));   // non-negative floats order as uints
     // ---- da / dgamma / dbeta: 8 warps -> smem -> one atomic per column per CTA
     __syncthreads();
 #pragma unroll
@@ -342,7 +347,7 @@ size_t encode_backward_workspace_bytes(const c2v_dims *d, int B, int L)
 {
     const size_t N = (size_t)B * L, H = d->encode, D = 2 * (size_t)d->terminal_embed + d->path_embed;
     const size_t Hs = (H + 3) / 4 * 4;
-    return align_up(N * H * 4, 1024) + align_up((size_t)B * 4, 1024) + align_up(D * Hs * 4, 1024) + 1024;
+    return align_up(N * H * 4, 1024) + align_up((size_t)B * 4, 1024) + align_up(D * Hs * 4, 1024) + 1024;   // last KB: dx absmax word
 }
 
 int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeArgs &a_in, int B,
@@ -364,6 +369,8 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     size_t o = align_up((size_t)a.N * a.H * 4, 1024);
     float *sb = reinterpret_cast<float *>(base + o); o += align_up((size_t)B * 4, 1024);
     float *w_t = reinterpret_cast<float *>(base + o); o += align_up((size_t)a.D * Hs * 4, 1024);
+    unsigned *dx_absmax = reinterpret_cast<unsigned *>(base + o);
+    C2V_CUDA_OK(cudaMemsetAsync(dx_absmax, 0, 4, st));
     memset(&a.ws, 0, sizeof(a.ws));
     a.ws.w_t = w_t;
     a.ws.status = nullptr;
@@ -372,7 +379,7 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     int rc = launch_transpose_w(p->input_linear, w_t, a.H, a.D, Hs, st);
     if (rc != C2V_OK) return rc;
     BackwardArgs b;
-    b.cv = cv; b.att = attention; b.d_cv = d_cv; b.d_att = d_att; b.sb = nullptr; b.x_stash = x_stash;
+    b.cv = cv; b.att = attention; b.d_cv = d_cv; b.d_att = d_att; b.sb = nullptr; b.x_stash = x_stash; b.dx_absmax = dx_absmax;
     b.W = p->input_linear; b.dx = dx;
     b.g_emb_t = g->terminal_embedding; b.g_emb_p = g->path_embedding;
     b.g_attn = g->attention; b.g_ln_g = g->ln_weight; b.g_ln_b = g->ln_bias;
@@ -407,7 +414,7 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     // dW = dX^T . C: tensor cores when the shape allows (c2v_backward_dw_tc.cu), C2V_BACKWARD_DW=ffma forces the CUDA cores
     const char *dw_env = getenv("C2V_BACKWARD_DW");
     if (backward_dw_tc_ok(a) && !(dw_env && !strcmp(dw_env, "ffma")))
-        return launch_backward_dw_tc(a, dx, g->input_linear, st);
+        return launch_backward_dw_tc(a, dx, dx_absmax, g->input_linear, st);
     const int gx = (a.D + DW_T - 1) / DW_T, gy = (a.H + DW_T - 1) / DW_T;
     long long split = (8LL * sms) / (gx * gy);
     if (split < 1) split = 1;

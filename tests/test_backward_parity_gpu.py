@@ -134,7 +134,9 @@ def test_tensor_core_dw_matches_the_cuda_core_gemm_at_many_tiles_per_cta():
                             tp["output_linear.weight"], tp["output_linear.bias"])
     s, pp, e = cuda(starts), cuda(paths), cuda(ends)
     cv, att = CF.encode_forward(dims, params, s, pp, e)
-    d_cv = cuda(rng.standard_normal((B, H)).astype(np.float32))
+    # gradients as small as a mean loss over a large batch makes them (|dx| ~ 1e-7: far below fp16's normal range;
+    # the kernel rescales dX by a power of two found from max |dx|)
+    d_cv = cuda((1e-6 * rng.standard_normal((B, H))).astype(np.float32))
     shapes = {"terminal_embedding": (T, E), "path_embedding": (P, E), "input_linear": (H, 3 * E), "ln_weight": (H,),
               "ln_bias": (H,), "attention": (H,)}
     os.environ["C2V_BACKWARD_DW"] = "ffma"
@@ -144,7 +146,7 @@ def test_tensor_core_dw_matches_the_cuda_core_gemm_at_many_tiles_per_cta():
         del os.environ["C2V_BACKWARD_DW"]
     g_tc = CF.encode_backward(dims, params, s, pp, e, cv, att, d_cv, None, shapes)
     a, b = g_tc["input_linear"].cpu().numpy(), g_ffma["input_linear"].cpu().numpy()
-    assert np.abs(b).max() > 1.0
+    assert 1e-8 < np.abs(b).max() < 1e-3
     assert np.abs(a - b).max() <= 2e-5 * np.abs(b).max()
     for k in ("terminal_embedding", "path_embedding", "ln_weight", "ln_bias", "attention"):
         assert torch.allclose(g_tc[k], g_ffma[k], rtol=0, atol=2e-5 * float(g_ffma[k].abs().max()))
