@@ -27,12 +27,17 @@ namespace c2v {
 
 int launch_transpose_w(const float *W, float *Wt, int H, int D, int Hs, cudaStream_t st);
 bool backward_dw_tc_ok(const EncodeArgs &a);
+bool backward_dc_tc_ok(const EncodeArgs &a);
+size_t backward_dc_tc_workspace_bytes();
+int launch_backward_dc_tc(const EncodeArgs &a, const float *W, const float *dx, const unsigned *dx_absmax, void *ws,
+                          float *g_emb_t, float *g_emb_p, cudaStream_t st);
 int launch_backward_dw_tc(const EncodeArgs &a, const float *dx, const unsigned *dx_absmax, float *dW, cudaStream_t st);
 
 struct BackwardArgs {
     const float *cv, *att, *d_cv, *d_att, *sb;   // sb[b] = sum_j att[b,j] d_att[b,j] (or null)
     const float *x_stash;                        // [N, H] x = c . W^T kept by the training forward (or null: recompute)
     unsigned *dx_absmax;                         // bits of max |dx| over the batch (atomicMax; for the fp16 split of K3b)
+    int skip_dc;                                 // dC = dX . W + scatter is done by K3c (c2v_backward_dc_tc.cu)
     const float *W;                              // [H, D] row-major (B operand of dC = dX . W)
     float *dx;                                   // [N, H]
     float *g_emb_t, *g_emb_p, *g_attn, *g_ln_g, *g_ln_b;
@@ -176,7 +181,7 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
         __syncthreads();
 
         // ---- dC = dX . W  (K = H), 128 columns of D at a time, scattered into the embedding grads
-        const int n_cb = (D + NB - 1) / NB, n_hc = (H + KC - 1) / KC;
+        const int n_cb = b.skip_dc ? 0 : (D + NB - 1) / NB, n_hc = (H + KC - 1) / KC;
         for (int cb = 0; cb < n_cb; ++cb) {
             float acc[4][8];
 #pragma unroll
@@ -347,7 +352,8 @@ size_t encode_backward_workspace_bytes(const c2v_dims *d, int B, int L)
 {
     const size_t N = (size_t)B * L, H = d->encode, D = 2 * (size_t)d->terminal_embed + d->path_embed;
     const size_t Hs = (H + 3) / 4 * 4;
-    return align_up(N * H * 4, 1024) + align_up((size_t)B * 4, 1024) + align_up(D * Hs * 4, 1024) + 1024;   // last KB: dx absmax word
+    return align_up(N * H * 4, 1024) + align_up((size_t)B * 4, 1024) + align_up(D * Hs * 4, 1024) + 1024 +   // 1 KB: dx absmax word
+           align_up(backward_dc_tc_workspace_bytes(), 1024);
 }
 
 int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeArgs &a_in, int B,
@@ -369,7 +375,8 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     size_t o = align_up((size_t)a.N * a.H * 4, 1024);
     float *sb = reinterpret_cast<float *>(base + o); o += align_up((size_t)B * 4, 1024);
     float *w_t = reinterpret_cast<float *>(base + o); o += align_up((size_t)a.D * Hs * 4, 1024);
-    unsigned *dx_absmax = reinterpret_cast<unsigned *>(base + o);
+    unsigned *dx_absmax = reinterpret_cast<unsigned *>(base + o); o += 1024;
+    void *dc_ws = base + o;
     C2V_CUDA_OK(cudaMemsetAsync(dx_absmax, 0, 4, st));
     memset(&a.ws, 0, sizeof(a.ws));
     a.ws.w_t = w_t;
@@ -380,6 +387,10 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     if (rc != C2V_OK) return rc;
     BackwardArgs b;
     b.cv = cv; b.att = attention; b.d_cv = d_cv; b.d_att = d_att; b.sb = nullptr; b.x_stash = x_stash; b.dx_absmax = dx_absmax;
+    // dC = dX . W and dW = dX^T . C run on the tensor cores when the shape allows; C2V_BACKWARD_DC / _DW = ffma force CUDA cores
+    const char *dc_env = getenv("C2V_BACKWARD_DC");
+    const bool dc_tc = backward_dc_tc_ok(a) && !(dc_env && !strcmp(dc_env, "ffma"));
+    b.skip_dc = dc_tc ? 1 : 0;
     b.W = p->input_linear; b.dx = dx;
     b.g_emb_t = g->terminal_embedding; b.g_emb_p = g->path_embedding;
     b.g_attn = g->attention; b.g_ln_g = g->ln_weight; b.g_ln_b = g->ln_bias;
@@ -410,6 +421,10 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     int grid = a.n_tiles < sms * occ ? a.n_tiles : sms * occ;
     kern<<<grid, THREADS, smem, st>>>(a, b, Hs);
     C2V_LAUNCH_OK("backward_rows_kernel");
+    if (dc_tc) {
+        rc = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st);
+        if (rc != C2V_OK) return rc;
+    }
 
     // dW = dX^T . C: tensor cores when the shape allows (c2v_backward_dw_tc.cu), C2V_BACKWARD_DW=ffma forces the CUDA cores
     const char *dw_env = getenv("C2V_BACKWARD_DW");

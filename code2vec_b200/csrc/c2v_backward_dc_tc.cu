@@ -1,0 +1,295 @@
+// c2v_backward_dc_tc.cu -- K3c: dC = dX . W on the tensor cores + scatter into the embedding gradients
+// (terminal_embed = path_embed = encode = 128).
+//
+// The gradient of the gathered context vectors (autograd of model.py:48-54 under loss.backward(), main.py:174):
+//   dC[r, d] = sum_h dX[r, h] * W[h, d],  then  dE_t[starts_r] += dC[r, 0:128], dE_p[paths_r] += dC[r, 128:256],
+//   dE_t[ends_r] += dC[r, 256:384]   (nn.Embedding's dense backward; PAD row 0 is a learned row and gets its share).
+// M = 128 context rows per tile (TMEM lanes), N = 384 = three 128-column accumulators (one per sub-vector), K = 128.
+// A = dX, K-major: the same [128 rows x 64 h] fp16 SWIZZLE_128B hi/lo panels the dW kernel builds (c2v_backward_dw_tc.cu),
+// read here with K-major descriptors.  B = W^T as a K-major image [128 d x 64 h] per (sub-vector, k-block), built once
+// per call by split_wt_kernel and streamed from L2 with 32 KB cp.async.bulk copies.  3-pass fp16 hi/lo split, fp32
+// accumulation in TMEM; dX is pre-scaled by the power of two from max |dx|, W by the one from max |W|.
+//
+// Warps: 0-3 scatter epilogue (thread = context row: tcgen05.ld -> 128-bit atomics into the three embedding rows) |
+// 4-19 dX producers | 20 MMA issuer | 21 W^T producer.  The three accumulators are released one by one, so the scatter
+// of sub-vector sv overlaps the MMAs of sv+1 (and of the next tile).
+#include <cuda_fp16.h>
+
+#include "c2v_tc_ptx.cuh"
+
+namespace c2v {
+
+namespace dct {
+constexpr int ROWS = 128, H = 128, E = 128, D = 3 * E;
+constexpr int PANEL = ROWS * 64 * 2;                  // 16 KB
+constexpr int A_STAGE = 4 * PANEL;                    // hi k0 | hi k1 | lo k0 | lo k1   (k-block = 64 h)
+constexpr int B_SLOT = 2 * PANEL;                     // hi | lo of one (sub-vector, k-block) tile of W^T
+constexpr int N_PROD_WARPS = 16, PROD_WARP0 = 4, MMA_WARP = 20, W_WARP = 21;
+constexpr int THREADS = 22 * 32;
+constexpr int ROWS_PER_PW = ROWS / N_PROD_WARPS;      // 8
+constexpr int NB = 6;                                 // W^T tiles per row tile: (sv, kb), kb minor
+constexpr int SMEM_A_OFF = 0, SMEM_B_OFF = 2 * A_STAGE, SMEM_BAR_OFF = SMEM_B_OFF + 2 * B_SLOT;
+constexpr int SMEM_BYTES = SMEM_BAR_OFF + 128 + 1024;
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);   // K-major A and B
+constexpr int IMG_BYTES = NB * B_SLOT;                // 192 KB
+}  // namespace dct
+
+// W [H=128][D=384] fp32 -> 6 tiles (sv * 2 + kb) of {hi, lo} [128 d x 64 h] fp16, K-major SWIZZLE_128B, scaled by the
+// power of two that lifts max |W| (bits in *absmax_bits, found by wt_absmax_kernel) just below 2^14.
+__global__ void wt_absmax_kernel(const float *__restrict__ W, unsigned *__restrict__ absmax_bits)
+{
+    float m = 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dct::H * dct::D; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(W[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(absmax_bits, __float_as_uint(m));
+}
+__global__ void __launch_bounds__(256)
+split_wt_kernel(const float *__restrict__ W, const unsigned *__restrict__ absmax_bits, uint8_t *__restrict__ img,
+                float *__restrict__ hdr)
+{
+    const float mx = __uint_as_float(*absmax_bits);
+    float scale = 1.0f;
+    if (mx > 0.0f && mx < 3.0e38f) {
+        int e;
+        frexpf(mx, &e);
+        int k = 14 - e;
+        k = k > 60 ? 60 : (k < -60 ? -60 : k);
+        scale = ldexpf(1.0f, k);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { hdr[0] = 1.0f / scale; hdr[1] = scale; }
+    // one thread = 4 consecutive d of one h (coalesced 16-B reads of W's rows)
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < dct::H * dct::D / 4; g += gridDim.x * blockDim.x) {
+        const int h = g / (dct::D / 4), d0 = (g % (dct::D / 4)) * 4;
+        const float4 w4 = *reinterpret_cast<const float4 *>(W + (size_t)h * dct::D + d0);
+        const float wv[4] = {w4.x * scale, w4.y * scale, w4.z * scale, w4.w * scale};
+        const int sv = d0 / dct::E, kb = h / 64, kk = h % 64;
+        uint8_t *base = img + (size_t)(sv * 2 + kb) * dct::B_SLOT;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const __half hi = __float2half_rn(wv[q]);
+            const __half lo = __float2half_rn(wv[q] - __half2float(hi));
+            const uint32_t off = sw128_offset(d0 % dct::E + q, kk);
+            *reinterpret_cast<__half *>(base + off) = hi;
+            *reinterpret_cast<__half *>(base + dct::PANEL + off) = lo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(dct::THREADS, 1)
+backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const unsigned *__restrict__ dx_absmax,
+                      const uint8_t *__restrict__ wt_img, const float *__restrict__ wt_hdr,
+                      float *__restrict__ g_emb_t, float *__restrict__ g_emb_p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    unsigned char *smem = smem_raw + (base - raw);
+    const uint32_t bars = base + dct::SMEM_BAR_OFF;
+    // a_full[2] @0, a_empty[2] @16, b_full[2] @32, b_empty[2] @48, t_full[3] @64, t_empty[3] @88, tmem ptr @112
+    const uint32_t bar_afull = bars, bar_aempty = bars + 16, bar_bfull = bars + 32, bar_bempty = bars + 48,
+                   bar_tfull = bars + 64, bar_tempty = bars + 88;
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + dct::SMEM_BAR_OFF + 112);
+    __shared__ long long s_status[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    long long *status = s_status;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_afull + 8 * s, 2 * dct::N_PROD_WARPS);
+            mbar_init(bar_aempty + 8 * s, 1);
+            mbar_init(bar_bfull + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, 1);
+        }
+        for (int s = 0; s < 3; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == dct::MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_ptr_smem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    float dx_scale = 1.0f;                              // power of two that lifts max |dx| just below 2^14 (see K3b)
+    {
+        const float mx = __uint_as_float(*dx_absmax);
+        if (mx > 0.0f && mx < 3.0e38f) {
+            int e;
+            frexpf(mx, &e);
+            int k = 14 - e;
+            k = k > 100 ? 100 : (k < -100 ? -100 : k);
+            dx_scale = ldexpf(1.0f, k);
+        }
+    }
+
+    if (warp >= dct::PROD_WARP0 && warp < dct::MMA_WARP) {
+        // =============================== dX PRODUCERS ===============================
+        const int pw = warp - dct::PROD_WARP0;
+        const int sub_row = lane >> 4, q = lane & 15;
+        uint32_t st_off[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = pw * dct::ROWS_PER_PW + 2 * j + sub_row;
+            st_off[j] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((q >> 1) ^ (r & 7)) & 7) << 4) + (q & 1) * 8);
+        }
+        const float4 *dx4 = reinterpret_cast<const float4 *>(dx);
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const long long row0 = ((long long)blockIdx.x + (long long)tl * gridDim.x) * dct::ROWS + pw * dct::ROWS_PER_PW;
+            const int as = tl & 1;
+            float4 buf[2][4];
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long r = row0 + 2 * j + sub_row;
+                    float4 v = r < a.N ? ldg_nc_v4(dx4 + (size_t)r * (dct::H / 4) + p * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v.x *= dx_scale; v.y *= dx_scale; v.z *= dx_scale; v.w *= dx_scale;
+                    buf[p][j] = v;
+                }
+            mbar_wait(bar_aempty + 8 * as, (((uint32_t)(tl >> 1)) & 1u) ^ 1u, status);
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const uint32_t hi = base + dct::SMEM_A_OFF + as * dct::A_STAGE + p * dct::PANEL, lo = hi + 2 * dct::PANEL;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = buf[p][j];
+                    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+                    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                    const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y);
+                    const __half2 l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+                    sts_v2(hi + st_off[j], pack_h2(h01), pack_h2(h23));
+                    sts_v2(lo + st_off[j], pack_h2(l01), pack_h2(l23));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_afull + 8 * as);
+            }
+        }
+    } else if (warp == dct::W_WARP) {
+        // =============================== W^T PRODUCER ===============================
+        if (lane == 0) {
+            const int n_items = my_tiles * dct::NB;
+            int kb6 = 0;
+            for (int it = 0; it < n_items; ++it) {
+                const int bs = it & 1;
+                mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(it >> 1)) & 1u) ^ 1u, status);
+                mbar_arrive_expect_tx(bar_bfull + 8 * bs, dct::B_SLOT);
+                bulk_copy_g2s(base + dct::SMEM_B_OFF + bs * dct::B_SLOT, wt_img + (size_t)kb6 * dct::B_SLOT, dct::B_SLOT, bar_bfull + 8 * bs);
+                if (++kb6 == dct::NB) kb6 = 0;
+            }
+        }
+        __syncwarp();
+    } else if (warp == dct::MMA_WARP) {
+        // =============================== MMA ISSUER (converged, one elected lane) ===============================
+        int it = 0;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const int as = tl & 1;
+            mbar_wait(bar_afull + 8 * as, ((uint32_t)(tl >> 1)) & 1u, status);
+#pragma unroll 1
+            for (int sv = 0; sv < 3; ++sv) {
+                mbar_wait(bar_tempty + 8 * sv, ((uint32_t)tl & 1u) ^ 1u, status);      // scatter of the previous tile drained
+#pragma unroll 1
+                for (int kb = 0; kb < 2; ++kb, ++it) {
+                    const int bs = it & 1;
+                    mbar_wait(bar_bfull + 8 * bs, ((uint32_t)(it >> 1)) & 1u, status);
+                    fence_proxy_async_smem();         // producers' generic-proxy stores of the dX panels -> async proxy
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t sa = base + dct::SMEM_A_OFF + as * dct::A_STAGE + kb * dct::PANEL;
+                        const uint32_t sb = base + dct::SMEM_B_OFF + bs * dct::B_SLOT;
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(sv * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + 2 * dct::PANEL + k * 32);
+                            const uint64_t b_hi = umma_desc(sb + k * 32), b_lo = umma_desc(sb + dct::PANEL + k * 32);
+                            umma_f16(d_tmem, a_hi, b_hi, dct::IDESC, (kb | k) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, a_lo, b_hi, dct::IDESC, 1u);
+                            umma_f16(d_tmem, a_hi, b_lo, dct::IDESC, 1u);
+                        }
+                        umma_commit(bar_bempty + 8 * bs);
+                        if (kb == 1) {
+                            umma_commit(bar_tfull + 8 * sv);
+                            if (sv == 2) umma_commit(bar_aempty + 8 * as);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // =============================== SCATTER EPILOGUE ===============================
+        const float inv = wt_hdr[0] / dx_scale;        // exact: both scales are powers of two
+        for (int tl = 0; tl < my_tiles; ++tl) {
+            const long long row = ((long long)blockIdx.x + (long long)tl * gridDim.x) * dct::ROWS + warp * 32 + lane;
+            long long is = 0, ip = 0, ie = 0;
+            const bool in_range = row < a.N;
+            if (in_range) { is = a.starts[row]; ip = a.paths[row]; ie = a.ends[row]; }
+            if (is < 0 || is >= a.T) is = 0;
+            if (ip < 0 || ip >= a.P) ip = 0;
+            if (ie < 0 || ie >= a.T) ie = 0;
+#pragma unroll 1
+            for (int sv = 0; sv < 3; ++sv) {
+                float *dst = sv == 1 ? g_emb_p + (size_t)ip * dct::E : g_emb_t + (size_t)(sv == 0 ? is : ie) * dct::E;
+                mbar_wait(bar_tfull + 8 * sv, (uint32_t)tl & 1u, status);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(sv * 128 + c * 32), v);
+                    tmem_ld_wait();
+                    if (c == 3) {                       // all 128 columns of this accumulator are in registers / done
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * sv);
+                    }
+                    if (in_range) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float v0 = v[j] * inv, v1 = v[j + 1] * inv, v2 = v[j + 2] * inv, v3 = v[j + 3] * inv;
+                            if (v0 != 0.0f || v1 != 0.0f || v2 != 0.0f || v3 != 0.0f)       // padded contexts: dx == 0
+                                atomicAdd(reinterpret_cast<float4 *>(dst + c * 32 + j), make_float4(v0, v1, v2, v3));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == dct::MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+bool backward_dc_tc_ok(const EncodeArgs &a) { return a.Et == dct::E && a.Ep == dct::E && a.H == dct::H; }
+size_t backward_dc_tc_workspace_bytes() { return 1024 + dct::IMG_BYTES; }
+
+// ws: [0, 1024) header {1/scale, scale} | W^T image
+int launch_backward_dc_tc(const EncodeArgs &a_in, const float *W, const float *dx, const unsigned *dx_absmax, void *ws,
+                          float *g_emb_t, float *g_emb_p, cudaStream_t st)
+{
+    EncodeArgs a = a_in;
+    a.n_tiles = (int)((a.N + dct::ROWS - 1) / dct::ROWS);
+    float *hdr = static_cast<float *>(ws);
+    uint8_t *img = static_cast<uint8_t *>(ws) + 1024;
+    unsigned *mxbits = reinterpret_cast<unsigned *>(static_cast<uint8_t *>(ws) + 512);
+    C2V_CUDA_OK(cudaMemsetAsync(mxbits, 0, 4, st));
+    wt_absmax_kernel<<<48, 256, 0, st>>>(W, mxbits);
+    C2V_LAUNCH_OK("wt_absmax_kernel");
+    split_wt_kernel<<<48, 256, 0, st>>>(W, mxbits, img, hdr);
+    C2V_LAUNCH_OK("split_wt_kernel");
+    int dev = 0, sms = 0;
+    C2V_CUDA_OK(cudaGetDevice(&dev));
+    C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    C2V_CUDA_OK(cudaFuncSetAttribute(backward_dc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dct::SMEM_BYTES));
+    int grid = a.n_tiles < sms ? a.n_tiles : sms;
+    if (grid < 1) grid = 1;
+    backward_dc_tc_kernel<<<grid, dct::THREADS, dct::SMEM_BYTES, st>>>(a, dx, dx_absmax, img, hdr, g_emb_t, g_emb_p);
+    C2V_LAUNCH_OK("backward_dc_tc_kernel");
+    return C2V_OK;
+}
+
+}  // namespace c2v

@@ -118,7 +118,8 @@ def test_one_adam_step_matches_reference_training_semantics():
 
 
 def test_tensor_core_dw_matches_the_cuda_core_gemm_at_many_tiles_per_cta():
-    """K3b (dW = dX^T . C on tcgen05, MN-major operands) against the CUDA-core kernel on 51,200 context rows = 400
+    """K3b (dW = dX^T . C on tcgen05, MN-major operands) and K3c (dC = dX . W + scatter into the embedding gradients)
+    against the CUDA-core kernels on 51,200 context rows = 400
     tiles (every CTA walks several tiles: operand stage / ring reuse and the TMEM-resident partial), ragged bags and an
     all-pad bag included; and against the fp64 product of the same dX on a slice of rows."""
     import os
@@ -139,11 +140,11 @@ def test_tensor_core_dw_matches_the_cuda_core_gemm_at_many_tiles_per_cta():
     d_cv = cuda((1e-6 * rng.standard_normal((B, H))).astype(np.float32))
     shapes = {"terminal_embedding": (T, E), "path_embedding": (P, E), "input_linear": (H, 3 * E), "ln_weight": (H,),
               "ln_bias": (H,), "attention": (H,)}
-    os.environ["C2V_BACKWARD_DW"] = "ffma"
+    os.environ["C2V_BACKWARD_DW"] = "ffma"; os.environ["C2V_BACKWARD_DC"] = "ffma"
     try:
         g_ffma = CF.encode_backward(dims, params, s, pp, e, cv, att, d_cv, None, shapes)
     finally:
-        del os.environ["C2V_BACKWARD_DW"]
+        del os.environ["C2V_BACKWARD_DW"]; del os.environ["C2V_BACKWARD_DC"]
     g_tc = CF.encode_backward(dims, params, s, pp, e, cv, att, d_cv, None, shapes)
     a, b = g_tc["input_linear"].cpu().numpy(), g_ffma["input_linear"].cpu().numpy()
     assert 1e-8 < np.abs(b).max() < 1e-3
