@@ -409,7 +409,7 @@ def main():
         import types
         import torch.nn.functional as F
         from code2vec_b200.model import Code2Vec
-        from code2vec_b200.distributed import FlatGradBucket, ddp_step
+        from code2vec_b200.distributed import FlatAdam, FlatGradBucket, ddp_step
         opt_ns = types.SimpleNamespace(terminal_count=w["T"], path_count=w["P"], label_count=C,
                                        terminal_embed_size=w["Et"], path_embed_size=w["Ep"], encode_size=H,
                                        dropout_prob=0.25, angular_margin_loss=False, angular_margin=0.5,
@@ -418,7 +418,7 @@ def main():
         model.load_state_dict(p)
         model = model.to(dev).train()
         bucket = FlatGradBucket(model.parameters())
-        optim = torch.optim.Adam(model.parameters(), lr=0.01, betas=(0.9, 0.999), fused=True)   # main.py:138 (single-kernel impl)
+        optim = FlatAdam(bucket, lr=0.01, betas=(0.9, 0.999))      # main.py:138 as one launch (c2v_adam_step; = torch's Adam)
         loss_fn = lambda o_, l_: F.nll_loss(F.log_softmax(o_, dim=1), l_)            # main.py:251-264
         def tstep(i):
             o = (i % nb) * B
@@ -437,7 +437,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         train = {"value": world * B * L * args.train_steps / (float(tt.item()) * 1e-3), "unit": "ctx/s",
                  "ms_per_step": float(tt.item()) / args.train_steps, "steps": args.train_steps,
-                 "step": "zero_grad + forward(dropout .25) + mean NLL + backward + 1 allreduce + dense Adam",
+                 "step": "forward(dropout .25) + mean NLL + backward + 1 allreduce + dense Adam with the zero_grad folded in (c2v_adam_step)",
                  "allreduce_bytes": bucket.nbytes(), "loss": float(last.item())}
         del model, optim, bucket
         torch.cuda.empty_cache()

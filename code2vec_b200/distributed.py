@@ -72,14 +72,64 @@ class FlatGradBucket:
                 self.flat.mul_(1.0 / dist.get_world_size())
 
 
+class FlatAdam:
+    """torch.optim.Adam(model.parameters(), lr, betas, weight_decay) (main.py:138) as ONE kernel launch per step
+    (`c2v_adam_step`): parameters, like the gradients of `bucket`, become views into one flat buffer; the step reads
+    p, g, m, v once, writes p, m, v and leaves the gradient zeroed for the next backward (main.py:171), folding the
+    1/world of the data-parallel mean into the read.  Dense, same update rule and operation order as torch's Adam."""
+
+    def __init__(self, bucket, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.bucket = bucket
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        flat = torch.empty_like(bucket.flat)
+        o = 0
+        for p in bucket.params:                                  # same order as the gradient bucket
+            n = p.numel()
+            flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = flat[o:o + n].view_as(p)
+            o += n
+        self.flat_param = flat
+        self.exp_avg = torch.zeros_like(flat)
+        self.exp_avg_sq = torch.zeros_like(flat)
+        self.t = 0
+
+    def step(self, grad_scale=1.0, zero_grad=True):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        self.t += 1
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        dev = self.flat_param.device
+        with torch.cuda.device(dev):
+            rc = lib.c2v_adam_step(P(self.flat_param), P(self.bucket.flat), P(self.exp_avg), P(self.exp_avg_sq),
+                                   self.flat_param.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                   self.weight_decay, self.t, float(grad_scale), 1 if zero_grad else 0,
+                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "c2v_adam_step")
+        # the kernel wrote through raw pointers: tell autograd (and the weight-image caches of the model, which key on
+        # Tensor._version) that every parameter changed, as an in-place torch op would
+        for p in self.bucket.params:
+            torch.autograd.graph.increment_version(p)
+
+    def zero_grad(self):
+        self.bucket.zero()
+
+
 def ddp_step(model, optimizer, bucket, starts, paths, ends, label, loss_fn):
     """One training step of main.py:171-175 on this rank's shard of the global batch."""
-    bucket.zero()
+    fused = isinstance(optimizer, FlatAdam)
+    if not fused:
+        bucket.zero()                       # (FlatAdam leaves the bucket zeroed at the end of its step)
     outputs, code_vector, attention = model.forward(starts, paths, ends, label)
     loss = loss_fn(outputs, label)
     loss.backward()
-    bucket.allreduce()
-    optimizer.step()
+    if fused:
+        bucket.allreduce(average=False)     # plain sum; the 1/world is folded into the optimizer's gradient read
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        optimizer.step(grad_scale=1.0 / world)
+    else:
+        bucket.allreduce()
+        optimizer.step()
     return loss
 
 

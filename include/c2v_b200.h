@@ -237,6 +237,14 @@ int c2v_build_batch(const int64_t *offsets, const int32_t *contexts, int64_t n_i
                     uint64_t seed, int64_t method_token, int64_t question_token, int64_t *starts,
                     int64_t *paths, int64_t *ends, int64_t *label, void *stream);
 
+/* Fused flat-buffer Adam: torch.optim.Adam(..., lr, betas, weight_decay) of main.py:138 +
+ * optimizer.step() (:175) + optimizer.zero_grad() (:171) for all parameters in one launch.  param / grad / exp_avg /
+ * exp_avg_sq: fp32 [n] device buffers, 16-byte aligned; `step` is the 1-based step count (bias corrections);
+ * the gradient is read as grad * grad_scale (1/world after a summing all_reduce) and, if zero_grad != 0, left zeroed. */
+int c2v_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                  int32_t zero_grad, void *stream);
+
 /* Counts kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t c2v_launch_count(void);
 

@@ -183,3 +183,26 @@ def test_stashed_x_equals_the_input_linear_output_and_gives_the_same_gradients(E
     for k in shapes:
         ref = g0[k].cpu().numpy()
         assert np.abs(g1[k].cpu().numpy() - ref).max() <= _tol(ref), k
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_flat_adam_matches_torch_adam_over_several_steps(wd):
+    """c2v_adam_step (one launch: Adam + zero_grad + 1/world) against torch.optim.Adam (main.py:138) driving the same
+    model through the same batches: parameters and losses agree step by step, the gradient bucket is left zeroed, and the
+    model's weight-image caches notice the update."""
+    from code2vec_b200.distributed import FlatAdam, FlatGradBucket, ddp_step
+    rec = load_golden("grad_cfg2")
+    s, pth, e, lab = (cuda(rec[k]) for k in ("starts", "paths", "ends", "label"))
+    lf = lambda o_, l_: F.nll_loss(F.log_softmax(o_, dim=1), l_)
+    m1 = model_from_golden(rec).train(); m2 = model_from_golden(rec).train()
+    b1 = FlatGradBucket(m1.parameters()); o1 = FlatAdam(b1, lr=0.01, betas=(0.9, 0.999), weight_decay=wd)
+    b2 = FlatGradBucket(m2.parameters()); o2 = torch.optim.Adam(m2.parameters(), lr=0.01, betas=(0.9, 0.999), weight_decay=wd)
+    for step in range(4):
+        l1 = ddp_step(m1, o1, b1, s, pth, e, lab, lf)
+        l2 = ddp_step(m2, o2, b2, s, pth, e, lab, lf)
+        assert abs(l1.item() - l2.item()) <= 2e-5 * max(1.0, abs(l2.item())), (step, l1.item(), l2.item())
+        assert float(b1.flat.abs().max()) == 0.0
+        for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+            assert n1 == n2
+            assert (p1 - p2).abs().max().item() <= 3e-6 * max(1.0, p2.abs().max().item()), (step, n1)
+    assert l1.item() < float(rec["loss"])            # it does learn
