@@ -44,6 +44,9 @@ struct BackwardArgs {
 };
 
 constexpr int MAXC = 8;   // columns per lane: encode_size <= 256
+// lane owns 4 consecutive columns per 128-column group (k = 0..3, 4..7): one Philox4x32 block gives the dropout masks of
+// all four (it is keyed by column / 4), and rows of X are read as one 16-byte piece per lane and group
+__device__ __forceinline__ int bk_col(int lane, int k) { return (k >> 2) * 128 + lane * 4 + (k & 3); }
 
 __global__ void bag_dot_kernel(const float *__restrict__ att, const float *__restrict__ d_att, int L,
                                float *__restrict__ sb)
@@ -84,7 +87,10 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
     long long *sidx = reinterpret_cast<long long *>(smem + lay.idx);
     float *Ac = reinterpret_cast<float *>(smem + lay.ac);
     float *Wc = reinterpret_cast<float *>(smem + lay.wc);
-    float *X = reinterpret_cast<float *>(smem + lay.x);
+    // lite mode (x from the stash, dC done by K3c): no GEMM operand buffers, so X moves up behind the reduction scratch
+    // and the CTA needs ~46 KB instead of ~85 KB of shared memory (4 CTAs per SM instead of 2)
+    const bool lite = b.x_stash != nullptr && b.skip_dc;
+    float *X = reinterpret_cast<float *>(smem + (lite ? lay.ac + 3 * 8 * Hs * 4 : lay.x));
     float *red = reinterpret_cast<float *>(smem + lay.ac);     // reused at the very end (3 x 8 warps x H)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -130,14 +136,19 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
             const float rstd = 1.0f / sqrtf(warp_sum(v) * invH + C2V_LN_EPS);
             float xh[MAXC], tt[MAXC], dm[MAXC];
             float dal = 0.0f, gvv = 0.0f;
+            uint4 dbits = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) {
-                const int c = lane + 32 * k;
+                const int c = bk_col(lane, k);
                 xh[k] = tt[k] = 0.0f; dm[k] = 1.0f;
                 if (c < H) {
                     xh[k] = (xr[c] - mean) * rstd;
                     tt[k] = tanh_accurate(fmaf(xh[k], a.ln_g[c], a.ln_b[c]));
-                    if (a.drop_p > 0.0f) dm[k] = dropout_mask_at(a.seed, row, c, a.drop_p, a.drop_scale);
+                    if (a.drop_p > 0.0f) {
+                        if ((k & 3) == 0) dbits = dropout_bits(a.seed, row, c >> 2);       // columns c .. c+3
+                        const unsigned w = (k & 3) == 0 ? dbits.x : (k & 3) == 1 ? dbits.y : (k & 3) == 2 ? dbits.z : dbits.w;
+                        dm[k] = dropout_mul(w, a.drop_p, a.drop_scale);
+                    }
                     dal = fmaf(gv[c], dm[k] * tt[k], dal);
                     gvv = fmaf(gv[c], cvb[c], gvv);
                 }
@@ -151,7 +162,7 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
             float m1 = 0.0f, m2 = 0.0f;
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) {
-                const int c = lane + 32 * k;
+                const int c = bk_col(lane, k);
                 dxh[k] = 0.0f;
                 if (c < H) {
                     const float h = dm[k] * tt[k];
@@ -168,7 +179,7 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
             m1 = warp_sum(m1) * invH; m2 = warp_sum(m2) * invH;
 #pragma unroll
             for (int k = 0; k < MAXC; ++k) {
-                const int c = lane + 32 * k;
+                const int c = bk_col(lane, k);
                 if (c < H) {
                     const float dxv = rstd * (dxh[k] - m1 - xh[k] * m2);
                     xr[c] = dxv;
@@ -264,7 +275,7 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < MAXC; ++k) {
-        const int c = lane + 32 * k;
+        const int c = bk_col(lane, k);
         if (c < H) {
             red[(0 * 8 + warp) * H + c] = acc_a[k];
             red[(1 * 8 + warp) * H + c] = acc_g[k];
@@ -278,6 +289,149 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
         for (int w = 0; w < 8; ++w) s += red[(which * 8 + w) * H + c];
         float *dst = which == 0 ? b.g_attn : which == 1 ? b.g_ln_g : b.g_ln_b;
         if (s != 0.0f) atomicAdd(dst + c, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// backward_rows_lite_kernel: the same per-row math when x comes from the forward's stash and dC / dW run on the tensor
+// cores (K3b, K3c), i.e. no GEMM in this kernel at all.  One warp per context row, rows strided over all warps; lane l
+// owns columns 4l..4l+3 of every 128-column group, so x, d_cv, cv and dx move as 16-byte pieces, gamma / beta / attn sit
+// in registers for the whole launch, one Philox block serves four columns, and padded contexts (attention weight
+// exactly 0) cost one zero store.  encode_size % 4 == 0, <= 256.
+// ------------------------------------------------------------------------------------
+template <int NG>                                             // 128-column groups: 1 (encode_size <= 128) or 2
+__global__ void __launch_bounds__(256, NG == 1 ? 4 : 2)
+backward_rows_lite_kernel(const EncodeArgs a, const BackwardArgs b)
+{
+    constexpr int MAXC = 4 * NG;
+    __shared__ float red[3 * 8 * 32 * MAXC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = a.H, L = a.L;
+    const float invH = 1.0f / (float)H;
+    float4 g4[NG], b4[NG], at4[NG];
+    bool on[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        const int c0 = g * 128 + lane * 4;
+        on[g] = c0 < H;
+        g4[g] = b4[g] = at4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on[g]) {
+            g4[g] = *reinterpret_cast<const float4 *>(a.ln_g + c0);
+            b4[g] = *reinterpret_cast<const float4 *>(a.ln_b + c0);
+            at4[g] = *reinterpret_cast<const float4 *>(a.attn + c0);
+        }
+    }
+    float acc_a[MAXC], acc_g[MAXC], acc_b[MAXC];
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) acc_a[k] = acc_g[k] = acc_b[k] = 0.0f;
+    float dx_max = 0.0f;
+    const long long n_warps = (long long)gridDim.x * 8;
+    for (long long row = (long long)blockIdx.x * 8 + warp; row < a.N; row += n_warps) {
+        const float alpha = b.att[row];
+        float4 *dxr = reinterpret_cast<float4 *>(b.dx + row * H);
+        if (alpha == 0.0f) {                                   // padded context of a bag with valid ones: dx == 0
+#pragma unroll
+            for (int g = 0; g < NG; ++g) if (on[g]) dxr[g * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const long long bag = row / L;
+        const float4 *xr = reinterpret_cast<const float4 *>(b.x_stash + row * H);
+        const float4 *gvp = reinterpret_cast<const float4 *>(b.d_cv + bag * H), *cvp = reinterpret_cast<const float4 *>(b.cv + bag * H);
+        float x[MAXC], gv[MAXC], cvv[MAXC];
+        float s = 0.0f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gg = xv, cc = xv;
+            if (on[g]) { xv = xr[g * 32 + lane]; gg = gvp[g * 32 + lane]; cc = cvp[g * 32 + lane]; }
+            x[4 * g] = xv.x; x[4 * g + 1] = xv.y; x[4 * g + 2] = xv.z; x[4 * g + 3] = xv.w;
+            gv[4 * g] = gg.x; gv[4 * g + 1] = gg.y; gv[4 * g + 2] = gg.z; gv[4 * g + 3] = gg.w;
+            cvv[4 * g] = cc.x; cvv[4 * g + 1] = cc.y; cvv[4 * g + 2] = cc.z; cvv[4 * g + 3] = cc.w;
+            s += (xv.x + xv.y) + (xv.z + xv.w);
+        }
+        const float mean = warp_sum(s) * invH;
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < MAXC; ++k) if (on[k >> 2]) { const float d = x[k] - mean; v = fmaf(d, d, v); }
+        const float rstd = 1.0f / sqrtf(warp_sum(v) * invH + C2V_LN_EPS);
+        float xh[MAXC], tt[MAXC], dm[MAXC];
+        float dal = 0.0f, gvv = 0.0f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+            if (on[g] && a.drop_p > 0.0f) bits = dropout_bits(a.seed, row, g * 32 + lane);
+            const float gam[4] = {g4[g].x, g4[g].y, g4[g].z, g4[g].w}, bet[4] = {b4[g].x, b4[g].y, b4[g].z, b4[g].w};
+            const unsigned bw[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = 4 * g + q;
+                xh[k] = tt[k] = 0.0f; dm[k] = 1.0f;
+                if (on[g]) {
+                    xh[k] = (x[k] - mean) * rstd;
+                    tt[k] = tanh_accurate(fmaf(xh[k], gam[q], bet[q]));
+                    if (a.drop_p > 0.0f) dm[k] = dropout_mul(bw[q], a.drop_p, a.drop_scale);
+                    dal = fmaf(gv[k], dm[k] * tt[k], dal);
+                    gvv = fmaf(gv[k], cvv[k], gvv);
+                }
+            }
+        }
+        dal = warp_sum(dal); gvv = warp_sum(gvv);
+        float extra = 0.0f, sbag = 0.0f;
+        if (b.d_att) { extra = b.d_att[row]; sbag = b.sb[bag]; }
+        const float dz = alpha * (dal + extra - gvv - sbag);
+        const float du = a.starts[row] > 0 ? dz : 0.0f;          // mask = starts > 0 (model.py:64)
+        float dxh[MAXC];
+        float m1 = 0.0f, m2 = 0.0f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const float gam[4] = {g4[g].x, g4[g].y, g4[g].z, g4[g].w}, att[4] = {at4[g].x, at4[g].y, at4[g].z, at4[g].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = 4 * g + q;
+                dxh[k] = 0.0f;
+                if (on[g]) {
+                    const float h = dm[k] * tt[k];
+                    const float dh = fmaf(alpha, gv[k], du * att[q]);
+                    acc_a[k] = fmaf(du, h, acc_a[k]);
+                    const float dy = dm[k] * dh * (1.0f - tt[k] * tt[k]);
+                    acc_g[k] = fmaf(dy, xh[k], acc_g[k]);
+                    acc_b[k] += dy;
+                    dxh[k] = dy * gam[q];
+                    m1 += dxh[k];
+                    m2 = fmaf(dxh[k], xh[k], m2);
+                }
+            }
+        }
+        m1 = warp_sum(m1) * invH; m2 = warp_sum(m2) * invH;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            if (!on[g]) continue;
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                o[q] = rstd * (dxh[4 * g + q] - m1 - xh[4 * g + q] * m2);
+                dx_max = fmaxf(dx_max, fabsf(o[q]));
+            }
+            dxr[g * 32 + lane] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    dx_max = warp_max(dx_max);
+    if (lane == 0 && dx_max > 0.0f) atomicMax(b.dx_absmax, __float_as_uint(dx_max));
+    // da / dgamma / dbeta: 8 warps -> smem -> one atomic per column per CTA
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+        red[((0 * 8 + warp) * MAXC + k) * 32 + lane] = acc_a[k];
+        red[((1 * 8 + warp) * MAXC + k) * 32 + lane] = acc_g[k];
+        red[((2 * 8 + warp) * MAXC + k) * 32 + lane] = acc_b[k];
+    }
+    __syncthreads();
+    for (int i = tid; i < 3 * MAXC * 32; i += 256) {
+        const int which = i / (MAXC * 32), k = (i / 32) % MAXC, l = i % 32;
+        const int c = bk_col(l, k);
+        if (c >= H) continue;
+        float sum = 0.0f;
+        for (int w = 0; w < 8; ++w) sum += red[((which * 8 + w) * MAXC + k) * 32 + l];
+        float *dst = which == 0 ? b.g_attn : which == 1 ? b.g_ln_g : b.g_ln_b;
+        if (sum != 0.0f) atomicAdd(dst + c, sum);
     }
 }
 
@@ -408,11 +562,25 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     int smem = lay.total;
     const int need_red = lay.ac + 3 * 8 * a.H * 4;
     if (need_red > smem) smem = need_red;
+    if (x_stash && dc_tc) smem = lay.ac + 3 * 8 * Hs * 4 + TM * Hs * 4;        // lite layout (see the kernel)
     if (smem > 227 * 1024) { set_error("backward: shared memory %d B too large", smem); return C2V_EUNSUPPORTED; }
     const bool vec = (a.Et % 4 == 0) && (a.Ep % 4 == 0);
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (x_stash && dc_tc && (a.H & 3) == 0) {                  // no GEMM left in this kernel: one warp per row
+        if (a.H <= 128) backward_rows_lite_kernel<1><<<sms * 16, 256, 0, st>>>(a, b);
+        else backward_rows_lite_kernel<2><<<sms * 8, 256, 0, st>>>(a, b);
+        C2V_LAUNCH_OK("backward_rows_lite_kernel");
+        rc = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st);
+        if (rc != C2V_OK) return rc;
+        const char *dw_env2 = getenv("C2V_BACKWARD_DW");
+        if (backward_dw_tc_ok(a) && !(dw_env2 && !strcmp(dw_env2, "ffma")))
+            return launch_backward_dw_tc(a, dx, dx_absmax, g->input_linear, st);
+        a.n_tiles = (int)((a.N + TM - 1) / TM);
+        goto dw_ffma;
+    }
+    {
     auto kern = vec ? backward_rows_kernel<true> : backward_rows_kernel<false>;
     C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 1;
@@ -430,6 +598,8 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     const char *dw_env = getenv("C2V_BACKWARD_DW");
     if (backward_dw_tc_ok(a) && !(dw_env && !strcmp(dw_env, "ffma")))
         return launch_backward_dw_tc(a, dx, dx_absmax, g->input_linear, st);
+    }
+dw_ffma:
     const int gx = (a.D + DW_T - 1) / DW_T, gy = (a.H + DW_T - 1) / DW_T;
     long long split = (8LL * sms) / (gx * gy);
     if (split < 1) split = 1;
