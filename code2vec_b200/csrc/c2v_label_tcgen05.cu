@@ -370,7 +370,10 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
 // K (= encode_size) is zero-padded to a multiple of 64 inside the operand images
 bool label_tcgen05_shape_ok(const c2v_dims *d) { return d->encode >= 4 && d->encode <= 256 && (d->encode & 3) == 0; }
 
-static size_t lt_keys_bytes(int B) { return ((size_t)B * 8 + 1023) / 1024 * 1024; }
+// ticket (first 64 bytes) + arg-max keys [B] u64.  This region sits AFTER the W_out image: the image is reused across calls
+// while the weights are unchanged (C2V_FLAG_REUSE_PREP), so its offset must not depend on the batch size (a ragged last
+// batch of an evaluation pass has a different B).
+static size_t lt_keys_bytes(int B) { return (64 + (size_t)B * 8 + 1023) / 1024 * 1024; }
 
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B)
 {
@@ -401,11 +404,14 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
     uint8_t *p = static_cast<uint8_t *>(ws);
     float *hdr = reinterpret_cast<float *>(p);
     unsigned *mxbits = reinterpret_cast<unsigned *>(p + 256);
-    unsigned *ticket = reinterpret_cast<unsigned *>(p + 512);
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(p + 1024);
+
     const size_t mt = (size_t)(B + 127) / 128, nt = (size_t)((C + 127) / 128);
     // W_out image first (reusable across calls while the weights are unchanged), then the cv image
-    uint8_t *imgB = p + 1024 + lt_keys_bytes(B), *imgA = imgB + nt * nkb * 2 * lt::TILE_BYTES;
+    uint8_t *imgB = p + 1024;                                           // batch-size independent offset
+    uint8_t *key_region = imgB + nt * nkb * 2 * lt::TILE_BYTES;
+    unsigned *ticket = reinterpret_cast<unsigned *>(key_region);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(key_region + 64);
+    uint8_t *imgA = key_region + lt_keys_bytes(B);
     const bool want_arg = argmax || maxval;
     const bool fused_arg = want_arg && mt <= (size_t)lt2::MAX_MT;
     int dev = 0, sms = 0;
@@ -419,10 +425,10 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
         split_rows_kernel<<<sms * 8, 256, 0, st>>>(Wout, C, H, nkb, mxbits, imgB, hdr, nullptr, 0);
         C2V_LAUNCH_OK("split_rows_kernel");
     }
-    // cv image (+ zeroes the ticket and the arg-max keys, which sit contiguously at p + 512)
+    // cv image (+ zeroes the ticket and the arg-max keys, which sit contiguously in key_region)
     C2V_CUDA_OK(launch_pdl(split_rows_kernel, dim3((unsigned)((mt * 128 * nkb * 16 + 255) / 256)), dim3(256), 0, st, cv,
                            (long long)B, H, nkb, (const unsigned *)nullptr, imgA, hdr,
-                           reinterpret_cast<unsigned long long *>(p + 512), fused_arg ? 64 + B : 0));
+                           reinterpret_cast<unsigned long long *>(key_region), fused_arg ? 8 + B : 0));
     C2V_COUNT_LAUNCH();
 
     C2V_CUDA_OK(cudaFuncSetAttribute(label_gemm_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt2::SMEM_BYTES));

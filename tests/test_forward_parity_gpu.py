@@ -376,3 +376,21 @@ def test_wide_configuration_full_shard_properties():
                                             p["path_embedding.weight"], p["input_linear.weight"],
                                             p["input_layer_norm.weight"], p["input_layer_norm.bias"], p["attention_parameter"])
     assert np.abs(v[sel] - ref_cv).max() <= EXPECT and np.abs(a[sel] - ref_att).max() <= EXPECT
+
+
+def test_weight_image_reuse_survives_a_smaller_last_batch():
+    """An evaluation pass ends with a ragged batch (main.py:162, drop_last unset): the cached W_out image (REUSE_PREP)
+    must be found again when B shrinks -- its workspace offset may not depend on the batch size."""
+    rng = np.random.default_rng(77)
+    C, H = 700, 128
+    w = cuda((rng.standard_normal((C, H)) * 0.3).astype(np.float32)); bias = cuda((0.1 * rng.standard_normal(C)).astype(np.float32))
+    dims = CF.make_dims(10, 10, C, H, H, H)
+    params = CF.make_params(None, None, None, None, None, None, w, bias)
+    cache = CF.PrepCache()
+    for B in (300, 7, 129, 1):
+        cvt = cuda(np.tanh(rng.standard_normal((B, H))).astype(np.float32))
+        out, am, mx = CF.label_logits_argmax(dims, params, cvt, cache=cache, weight=w)
+        ref = CF.label_logits(dims, params, cvt)                       # fresh workspace, images rebuilt
+        assert torch.equal(out, ref)
+        tv, ti = torch.max(ref, dim=1)
+        assert torch.equal(mx, tv) and torch.equal(am, ti)
