@@ -1,11 +1,26 @@
 """torch-facing wrappers over the C ABI: device memory, streams and autograd plumbing only.
 All arithmetic happens inside libc2v_b200.so."""
 import ctypes
+import os
 
 import torch
 
 from . import _lib
 from ._lib import Dims, Dropout, Grads, Params
+
+
+# C2V_POISON=1: every buffer handed to the library uninitialised (workspaces, outputs, stashes) is filled with 0xFF bytes
+# (fp32 NaN / int -1) first, so that a read of memory the current call did not write shows up as NaN instead of hiding
+# behind whatever an earlier, identical call left there (debugging aid).
+_POISON = os.environ.get("C2V_POISON", "0") == "1"
+
+
+def _empty(shape, dtype, device):
+    t = torch.empty(shape, dtype=dtype, device=device)
+    if _POISON:
+        if t.numel():
+            t.reshape(-1).view(torch.uint8).fill_(255)
+    return t
 
 
 def _ptr(t):
@@ -59,7 +74,7 @@ class PrepCache:
         key = (weight.data_ptr(), weight._version, str(device))
         fresh = self.buf is None or self.buf.numel() < nbytes or self.buf.device != device
         if fresh:
-            self.buf = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+            self.buf = _empty((nbytes,), torch.uint8, device)
         reuse = (not fresh) and key == self.key
         self.key = key
         return self.buf, reuse
@@ -76,17 +91,17 @@ def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False
     starts = _idx(starts, "starts"); paths = _idx(paths, "paths", (B, L)); ends = _idx(ends, "ends", (B, L))
     dev = starts.device
     with torch.cuda.device(dev):
-        cv = torch.empty((B, dims.encode), dtype=torch.float32, device=dev)
-        att = torch.empty((B, L), dtype=torch.float32, device=dev)
+        cv = _empty((B, dims.encode), torch.float32, dev)
+        att = _empty((B, L), torch.float32, dev)
         nbytes = lib.c2v_encode_workspace_bytes(ctypes.byref(dims), B, L)
         if cache is not None and weight is not None:
             ws, reuse = cache.get(nbytes, dev, weight)
             if reuse:
                 algo = int(algo) | REUSE_PREP
         else:
-            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            ws = _empty((nbytes,), torch.uint8, dev)
         drop = Dropout(float(drop_p), 1 if training else 0, int(seed))
-        xs = torch.empty((B * L, dims.encode), dtype=torch.float32, device=dev) if stash else None
+        xs = _empty((B * L, dims.encode), torch.float32, dev) if stash else None
         rc = lib.c2v_encode_forward_stash(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
                                           B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(xs), _ptr(ws), ws.numel(),
                                           int(algo), _stream(dev))
@@ -109,14 +124,14 @@ def label_logits(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weight=None)
     B = cv.shape[0]
     dev = cv.device
     with torch.cuda.device(dev):
-        out = torch.empty((B, dims.label_count), dtype=torch.float32, device=dev)
+        out = _empty((B, dims.label_count), torch.float32, dev)
         nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
         if cache is not None and weight is not None:
             ws, reuse = cache.get(nbytes, dev, weight)
             if reuse:
                 algo = int(algo) | REUSE_PREP
         else:
-            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            ws = _empty((nbytes,), torch.uint8, dev)
         rc = lib.c2v_label_logits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), B, _ptr(out),
                                   _ptr(ws), ws.numel(), int(algo), _stream(dev))
         _lib.check(rc, "c2v_label_logits")
@@ -130,16 +145,16 @@ def label_logits_argmax(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weigh
     B = cv.shape[0]
     dev = cv.device
     with torch.cuda.device(dev):
-        out = torch.empty((B, dims.label_count), dtype=torch.float32, device=dev)
-        am = torch.empty((B,), dtype=torch.int64, device=dev)
-        mx = torch.empty((B,), dtype=torch.float32, device=dev)
+        out = _empty((B, dims.label_count), torch.float32, dev)
+        am = _empty((B,), torch.int64, dev)
+        mx = _empty((B,), torch.float32, dev)
         nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
         if cache is not None and weight is not None:
             ws, reuse = cache.get(nbytes, dev, weight)
             if reuse:
                 algo = int(algo) | REUSE_PREP
         else:
-            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            ws = _empty((nbytes,), torch.uint8, dev)
         rc = lib.c2v_label_logits_argmax(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), B, _ptr(out),
                                          _ptr(am), _ptr(mx), _ptr(ws), ws.numel(), int(algo), _stream(dev))
         _lib.check(rc, "c2v_label_logits_argmax")
@@ -154,7 +169,7 @@ def angular_logits(dims, params, cv, label, margin, inverse_temp):
     dev = cv.device
     label = _idx(label, "label", (B,))
     with torch.cuda.device(dev):
-        out = torch.empty((B, dims.label_count), dtype=torch.float32, device=dev)
+        out = _empty((B, dims.label_count), torch.float32, dev)
         rc = lib.c2v_angular_logits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), _ptr(label), B,
                                     float(margin), float(inverse_temp), _ptr(out), _stream(dev))
         _lib.check(rc, "c2v_angular_logits")
@@ -169,9 +184,9 @@ def loss_argmax(outputs, label=None, want_grad=False):
     dev = outputs.device
     outputs = outputs.contiguous()
     with torch.cuda.device(dev):
-        am = torch.empty((B,), dtype=torch.int64, device=dev)
-        mx = torch.empty((B,), dtype=torch.float32, device=dev)
-        loss = torch.empty((), dtype=torch.float32, device=dev) if label is not None else None
+        am = _empty((B,), torch.int64, dev)
+        mx = _empty((B,), torch.float32, dev)
+        loss = _empty((), torch.float32, dev) if label is not None else None
         dout = torch.empty_like(outputs) if (want_grad and label is not None) else None
         if label is not None:
             label = _idx(label, "label", (B,))
@@ -187,8 +202,8 @@ def label_backward(dims, params, cv, d_out, need_cv=True, need_w=True, need_b=Tr
     dev = cv.device
     with torch.cuda.device(dev):
         d_cv = torch.empty_like(cv) if need_cv else None
-        d_w = torch.empty((dims.label_count, dims.encode), dtype=torch.float32, device=dev) if need_w else None
-        d_b = torch.empty((dims.label_count,), dtype=torch.float32, device=dev) if need_b else None
+        d_w = _empty((dims.label_count, dims.encode), torch.float32, dev) if need_w else None
+        d_b = _empty((dims.label_count,), torch.float32, dev) if need_b else None
         rc = lib.c2v_label_backward(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()),
                                     _ptr(d_out.contiguous()), B, _ptr(d_cv), _ptr(d_w), _ptr(d_b), _stream(dev))
         _lib.check(rc, "c2v_label_backward")
@@ -207,7 +222,7 @@ def encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, sha
         grads = Grads(_ptr(g["terminal_embedding"]), _ptr(g["path_embedding"]), _ptr(g["input_linear"]),
                       _ptr(g["ln_weight"]), _ptr(g["ln_bias"]), _ptr(g["attention"]))
         nbytes = lib.c2v_encode_backward_workspace_bytes(ctypes.byref(dims), B, L)
-        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        ws = _empty((nbytes,), torch.uint8, dev)
         drop = Dropout(float(drop_p), 1 if training else 0, int(seed))
         rc = lib.c2v_encode_backward_stashed(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
                                              B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(x_stash),
