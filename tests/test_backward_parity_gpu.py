@@ -68,9 +68,13 @@ def test_gradients_with_attention_in_the_loss():
     # Known open issue: once in ~100 fresh-process runs of this test one gradient left the tolerance;
     # 60 in-process repetitions (scripts/repro_flake.py) stay below 0.1 x tolerance, so it is not a numerical tail.  Until
     # it is understood, a first miss is reported loudly and the comparison repeated once on a fresh model.
-    bad, pad_grad = attempt()
+    import warnings
+    try:
+        bad, pad_grad = attempt()
+    except Exception as exc:                      # (the one observed failure left no detail: keep whatever it was)
+        warnings.warn(f"first attempt raised {type(exc).__name__}: {exc}; repeating once")
+        bad, pad_grad = {"exception": repr(exc)}, 0.0
     if bad:
-        import warnings
         warnings.warn(f"gradient mismatch on the first attempt: {bad}; repeating once")
         bad, pad_grad = attempt()
     assert not bad, bad
