@@ -41,6 +41,11 @@ class DeviceInfo(ctypes.Structure):
                 ("global_mem_bytes", c_i64), ("smem_per_block_optin", c_i64)]
 
 
+class CorpusInfo(ctypes.Structure):
+    _fields_ = [("n_items", c_i64), ("n_contexts", c_i64), ("n_aliases", c_i64), ("label_bytes", c_i64),
+                ("alias_bytes", c_i64), ("alias_name_bytes", c_i64)]
+
+
 # every symbol include/c2v_b200.h declares: (restype, argtypes)
 _P = ctypes.POINTER
 SYMBOLS = {
@@ -79,6 +84,16 @@ SYMBOLS = {
     "c2v_launch_count": (c_i64, []),
     "c2v_profile_enable": (ctypes.c_int, [c_i32]),
     "c2v_profile_read": (ctypes.c_int, [_P(ctypes.c_double), _P(c_i64)]),
+    "c2v_corpus_parse_buffer": (ctypes.c_int, [ctypes.c_char_p, c_sz, c_i32, _P(c_vp)]),
+    "c2v_corpus_parse_files": (ctypes.c_int, [_P(ctypes.c_char_p), c_i32, c_i32, _P(c_vp)]),
+    "c2v_corpus_free": (None, [c_vp]),
+    "c2v_corpus_get_info": (ctypes.c_int, [c_vp, _P(CorpusInfo)]),
+    "c2v_corpus_export": (ctypes.c_int, [c_vp] + [c_vp] * 12),
+    "c2v_corpus_save": (ctypes.c_int, [c_vp, ctypes.c_char_p]),
+    "c2v_corpus_load": (ctypes.c_int, [ctypes.c_char_p, _P(c_vp)]),
+    "c2v_format_float": (ctypes.c_int, [c_f32, ctypes.c_char_p, c_sz]),
+    "c2v_write_code_vectors": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp,
+                                              c_i64, ctypes.c_char_p, ctypes.c_char_p, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

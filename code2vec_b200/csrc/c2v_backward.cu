@@ -65,13 +65,15 @@ __device__ __forceinline__ void load_wrow_chunk(const float *__restrict__ W, int
         const int kk = i / (NB / 4), cq = i % (NB / 4);
         const int h = hc * KC + kk, col = cb * NB + cq * 4;
         float *dst = Wc + kk * NB + cq * 4;
-        if (h < H && col + 3 < D) cp_async16(dst, W + (size_t)h * D + col);
+        // 16-byte copies only when every row of W starts 16-byte aligned (D % 4 == 0: the rows are D floats apart)
+        if (h < H && col + 3 < D && (D & 3) == 0) cp_async16(dst, W + (size_t)h * D + col);
         else {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (h < H) {
                 if (col < D) v.x = W[(size_t)h * D + col];
                 if (col + 1 < D) v.y = W[(size_t)h * D + col + 1];
                 if (col + 2 < D) v.z = W[(size_t)h * D + col + 2];
+                if (col + 3 < D) v.w = W[(size_t)h * D + col + 3];
             }
             *reinterpret_cast<float4 *>(dst) = v;
         }

@@ -163,6 +163,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                     sts_v2(hi + st_off[j], pack_h2(h01), pack_h2(h23));
                     sts_v2(lo + st_off[j], pack_h2(l01), pack_h2(l23));
                 }
+                fence_proxy_async_smem();             // writer side: generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_afull + 8 * as);
             }

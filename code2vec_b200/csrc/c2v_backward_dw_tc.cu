@@ -143,6 +143,7 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                 }
                 const uint32_t hi = base + dwt::SMEM_A_OFF + as * dwt::A_STAGE + p * dwt::PANEL;
                 split_store(hi, hi + 2 * dwt::PANEL, buf);
+                fence_proxy_async_smem();             // writer side: generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_afull + 8 * as);
             }
@@ -163,6 +164,7 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                 mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(itb >> 1)) & 1u) ^ 1u, status);
                 const uint32_t hi = base + dwt::SMEM_B_OFF + bs * dwt::B_SLOT;
                 split_store(hi, hi + dwt::PANEL, buf);
+                fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_bfull + 8 * bs);
             }

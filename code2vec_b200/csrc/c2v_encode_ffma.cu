@@ -70,6 +70,7 @@ encode_ffma_kernel(const EncodeArgs a, const int Hs)
                 const int r = i / a.H, c = i % a.H;
                 if (row0 + r < a.N) a.stash_x[(size_t)(row0 + r) * a.H + c] = X[r * Hs + c];
             }
+            __syncthreads();                                 // the per-row loop below overwrites X in place (tanh output)
         }
 
         // ---- LayerNorm + tanh (+dropout) + score, one warp per row (model.py:55-61, 92-93)

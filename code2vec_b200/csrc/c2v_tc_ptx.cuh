@@ -53,6 +53,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, long lo
 #if C2V_SPIN_NS > 0
         __nanosleep(C2V_SPIN_NS);
 #endif
+#ifndef C2V_NO_WATCHDOG                               // (compute-sanitizer slows kernels 100x: build the variant without it)
         if ((spins & 0x3ff) == 0x3ff) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
@@ -62,6 +63,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, long lo
                 __trap();
             }
         }
+#endif
     }
 }
 __device__ __forceinline__ bool elect_one() {

@@ -138,3 +138,6 @@ def broadcast_parameters(model, src=0):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, src)
+            # a write through .data does not bump Tensor._version, which the model's cached weight images
+            # (functional.PrepCache) are keyed on: bump it so the next forward rebuilds them
+            torch.autograd.graph.increment_version(t)

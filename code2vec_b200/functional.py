@@ -39,6 +39,13 @@ def _need_cuda(*tensors):
                 f"{t.device} tensor. Move the module and its inputs to a B200 device.")
 
 
+def _f32c(t, name):
+    """contiguous fp32 CUDA tensor (the caller keeps the returned object alive across the library call)"""
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError(f"{name} must be a float32 CUDA tensor, got {t.dtype} on {t.device}")
+    return t.contiguous()
+
+
 def _idx(t, name, shape=None):
     if t.dtype != torch.int64:
         raise TypeError(f"{name} must be int64 (dataset_builder.py:206-209), got {t.dtype}")
@@ -132,7 +139,8 @@ def label_logits(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weight=None)
                 algo = int(algo) | REUSE_PREP
         else:
             ws = _empty((nbytes,), torch.uint8, dev)
-        rc = lib.c2v_label_logits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), B, _ptr(out),
+        cv = _f32c(cv, "code_vector")          # bound to a local: the pointer must outlive the launch
+        rc = lib.c2v_label_logits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv), B, _ptr(out),
                                   _ptr(ws), ws.numel(), int(algo), _stream(dev))
         _lib.check(rc, "c2v_label_logits")
     return out
@@ -155,7 +163,8 @@ def label_logits_argmax(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weigh
                 algo = int(algo) | REUSE_PREP
         else:
             ws = _empty((nbytes,), torch.uint8, dev)
-        rc = lib.c2v_label_logits_argmax(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), B, _ptr(out),
+        cv = _f32c(cv, "code_vector")
+        rc = lib.c2v_label_logits_argmax(ctypes.byref(dims), ctypes.byref(params), _ptr(cv), B, _ptr(out),
                                          _ptr(am), _ptr(mx), _ptr(ws), ws.numel(), int(algo), _stream(dev))
         _lib.check(rc, "c2v_label_logits_argmax")
     return out, am, mx
@@ -170,7 +179,8 @@ def angular_logits(dims, params, cv, label, margin, inverse_temp):
     label = _idx(label, "label", (B,))
     with torch.cuda.device(dev):
         out = _empty((B, dims.label_count), torch.float32, dev)
-        rc = lib.c2v_angular_logits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()), _ptr(label), B,
+        cv = _f32c(cv, "code_vector")
+        rc = lib.c2v_angular_logits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv), _ptr(label), B,
                                     float(margin), float(inverse_temp), _ptr(out), _stream(dev))
         _lib.check(rc, "c2v_angular_logits")
     return out
@@ -204,8 +214,9 @@ def label_backward(dims, params, cv, d_out, need_cv=True, need_w=True, need_b=Tr
         d_cv = torch.empty_like(cv) if need_cv else None
         d_w = _empty((dims.label_count, dims.encode), torch.float32, dev) if need_w else None
         d_b = _empty((dims.label_count,), torch.float32, dev) if need_b else None
-        rc = lib.c2v_label_backward(ctypes.byref(dims), ctypes.byref(params), _ptr(cv.contiguous()),
-                                    _ptr(d_out.contiguous()), B, _ptr(d_cv), _ptr(d_w), _ptr(d_b), _stream(dev))
+        cv = _f32c(cv, "code_vector"); d_out = _f32c(d_out, "d_outputs")
+        rc = lib.c2v_label_backward(ctypes.byref(dims), ctypes.byref(params), _ptr(cv),
+                                    _ptr(d_out), B, _ptr(d_cv), _ptr(d_w), _ptr(d_b), _stream(dev))
         _lib.check(rc, "c2v_label_backward")
     return d_cv, d_w, d_b
 
@@ -224,10 +235,13 @@ def encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, sha
         nbytes = lib.c2v_encode_backward_workspace_bytes(ctypes.byref(dims), B, L)
         ws = _empty((nbytes,), torch.uint8, dev)
         drop = Dropout(float(drop_p), 1 if training else 0, int(seed))
+        # contiguous copies (if any were needed) are bound to locals so that they outlive the launch
+        cv = _f32c(cv, "code_vector"); att = _f32c(att, "attention")
+        d_cv = _f32c(d_cv, "d_code_vector")
+        d_att = _f32c(d_att, "d_attention") if d_att is not None else None
         rc = lib.c2v_encode_backward_stashed(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
                                              B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(x_stash),
-                                             _ptr(d_cv.contiguous()),
-                                             _ptr(d_att.contiguous()) if d_att is not None else None, ctypes.byref(grads),
+                                             _ptr(d_cv), _ptr(d_att), ctypes.byref(grads),
                                              _ptr(ws), nbytes, _stream(dev))
         _lib.check(rc, "c2v_encode_backward")
     return g

@@ -245,6 +245,43 @@ int c2v_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, 
                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                   int32_t zero_grad, void *stream);
 
+/* ---- corpus reader / code-vector writer: the data formats either side of the path ----------
+ * c2v_corpus_parse_*: DatasetReader.load (/root/reference/model/dataset_reader.py:72-128) for the `corpus.txt` format
+ * (`#id`, `label:`, `class:`, `paths:` + `start\tpath\tend` lines, `vars:` + `original\talias` lines, blank line between
+ * items).  Several files are read as one concatenated stream (README: `cat splitted_corpus_*`).  question_shift =
+ * QUESTION_TOKEN_INDEX (dataset_reader.py:11, added to start and end, :113-115).  A malformed line is C2V_EINVAL with
+ * the line number in c2v_last_error() (the reference raises ValueError / IndexError there).  Host-only: no GPU needed. */
+typedef struct c2v_corpus c2v_corpus;
+typedef struct c2v_corpus_info {
+    int64_t n_items, n_contexts, n_aliases, label_bytes, alias_bytes, alias_name_bytes;
+} c2v_corpus_info;
+int c2v_corpus_parse_buffer(const char *text, size_t n, int32_t question_shift, c2v_corpus **out);
+int c2v_corpus_parse_files(const char *const *paths, int32_t n_paths, int32_t question_shift, c2v_corpus **out);
+void c2v_corpus_free(c2v_corpus *c);
+int c2v_corpus_get_info(const c2v_corpus *c, c2v_corpus_info *info);
+/* Copies the parsed corpus into caller buffers (any pointer may be NULL = skip): ids [n_items] (-1: no `#` line),
+ * ctx_offsets [n_items+1], contexts int32 [n_contexts][3] (the CSR image c2v_build_batch reads), label_offsets
+ * [n_items+1] + label_blob (raw text after `label:`), has_label [n_items], label_pos [n_items] (aliases of the item that
+ * precede its label line: vocabulary insertion order), alias_item_offsets [n_items+1], and per alias the original
+ * variable name (alias_orig_offsets [n_aliases+1] + alias_blob) and the alias (alias_name_offsets + alias_name_blob). */
+int c2v_corpus_export(const c2v_corpus *c, int64_t *ids, int64_t *ctx_offsets, int32_t *contexts,
+                      int64_t *label_offsets, char *label_blob, uint8_t *has_label, int32_t *label_pos,
+                      int64_t *alias_item_offsets, int64_t *alias_orig_offsets, char *alias_blob,
+                      int64_t *alias_name_offsets, char *alias_name_blob);
+/* Binary cache of a parsed corpus (one flat little-endian file). */
+int c2v_corpus_save(const c2v_corpus *c, const char *path);
+int c2v_corpus_load(const char *path, c2v_corpus **out);
+/* Python's str(float) of an fp32 value (shortest round trip of the double it converts to); returns the length. */
+int c2v_format_float(float value, char *out, size_t out_bytes);
+/* write_code_vectors (/root/reference/main.py:393-423) for n rows: vector file lines `name\tv0 v1 ...` (:416) opened
+ * with `mode` ("w" / "a"), preceded by the `n_items\tencode_size` header (main.py:227-228) when header_items >= 0; and,
+ * when result_path != NULL, the test TSV `id\tTrue|False\tlabel\tpred\tmax_logit` (:420).  All pointers are HOST
+ * memory; label / pred_label index the vocabulary given as names_blob + name_offsets [n_names+1]. */
+int c2v_write_code_vectors(const char *vector_path, const char *mode, int64_t header_items, int64_t n, int32_t H,
+                           const float *code_vectors, const int64_t *label, const char *names_blob,
+                           const int64_t *name_offsets, int64_t n_names, const char *result_path, const char *result_mode,
+                           const int64_t *ids, const int64_t *pred_label, const float *pred_score);
+
 /* Counts kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t c2v_launch_count(void);
 
