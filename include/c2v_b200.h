@@ -237,6 +237,20 @@ int c2v_build_batch(const int64_t *offsets, const int32_t *contexts, int64_t n_i
                     uint64_t seed, int64_t method_token, int64_t question_token, int64_t *starts,
                     int64_t *paths, int64_t *ends, int64_t *label, void *stream);
 
+/* The variable-name task of the same builder (/root/reference/model/dataset_builder.py:152-204, `--infer_variable_name`):
+ * a unit is an (item, @var_k alias) pair -- unit_item / unit_var (terminal index of @var_k) / unit_label [n_units], in the
+ * reference's order (items in order, aliases in CodeData.aliases order).  Row b of the outputs is the bag of unit
+ * unit_ids[b]: the contexts of the item whose start or end is @var_k, @var_k rewritten to @question (:181-182, :190-191),
+ * every other token t with var_pos[t] >= 0 mapped to variable_indexes[sigma(var_pos[t])] when shuffle_variable_indexes
+ * != 0 (sigma: a per-(seed, item) permutation, :166-168; var_pos is int32 [terminal_count], -1 for non-variables), a
+ * uniformly random subset of min(n, L) of them (:193-195) and a zero-padded suffix (:196-198). */
+int c2v_build_batch_vars(const int64_t *offsets, const int32_t *contexts, int64_t n_items,
+                         const int64_t *unit_item, const int64_t *unit_var, const int64_t *unit_label,
+                         int64_t n_units, const int64_t *unit_ids, int32_t B, int32_t L, uint64_t seed,
+                         int64_t question_token, const int32_t *var_pos, int64_t terminal_count,
+                         const int64_t *variable_indexes, int32_t n_vars, int32_t shuffle_variable_indexes,
+                         int64_t *starts, int64_t *paths, int64_t *ends, int64_t *label, void *stream);
+
 /* Fused flat-buffer Adam: torch.optim.Adam(..., lr, betas, weight_decay) of main.py:138 +
  * optimizer.step() (:175) + optimizer.zero_grad() (:171) for all parameters in one launch.  param / grad / exp_avg /
  * exp_avg_sq: fp32 [n] device buffers, 16-byte aligned; `step` is the 1-based step count (bias corrections);

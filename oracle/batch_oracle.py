@@ -64,3 +64,48 @@ def build_batch(offsets, contexts, item_ids, L, seed, method_token, question_tok
         e[e == method_token] = question_token          # :142-143
         out[0, b, :len(sel)] = s; out[1, b, :len(sel)] = p; out[2, b, :len(sel)] = e
     return out[0], out[1], out[2]
+
+
+# ---- variable-name task (dataset_builder.py:152-204, infer_variable branch) -------------------------------------------
+def var_permutation(seed, item, n_vars):
+    """sigma: position i of `variable_indexes` is replaced by variable_indexes[sigma[i]] (:166-168 shuffle, re-derived
+    from a counter-based hash like everything else here): argsort of key(i) = hash(seed ^ A5.., item, i), ties by i."""
+    with np.errstate(over="ignore"):
+        vbase = _mix64(np.array([np.uint64(seed) ^ np.uint64(0xA5A5A5A55A5A5A5A) ^
+                                 (np.uint64(item) * np.uint64(0xD1B54A32D192ED03) & _M64)], dtype=np.uint64))[0]
+        i = np.arange(n_vars, dtype=np.uint64)
+        k = (_mix64(vbase ^ (i * np.uint64(0x8CB92BA72F3D8DD7) & _M64)) >> np.uint64(32)).astype(np.uint32)
+    return np.lexsort((np.arange(n_vars), k)).astype(np.int64)
+
+
+def build_batch_vars(offsets, contexts, unit_item, unit_var, unit_ids, L, seed, question_token, variable_indexes=None,
+                     shuffle_variable_indexes=False):
+    """-> starts, paths, ends int64 [B, L]: row b = the contexts of item unit_item[u] that touch token unit_var[u]
+    (u = unit_ids[b]), @var -> @question, other variables permuted per item if asked, min(n, L) of them chosen by the
+    smallest (key, j) with key = hash(seed, item, var, j), kept in stored order, zero suffix."""
+    B = len(unit_ids)
+    out = np.zeros((3, B, L), dtype=np.int64)
+    var = None if variable_indexes is None else np.asarray(variable_indexes, dtype=np.int64)
+    for b, u in enumerate(np.asarray(unit_ids, dtype=np.int64)):
+        item, v = int(unit_item[u]), int(unit_var[u])
+        lo, hi = int(offsets[item]), int(offsets[item + 1])
+        c = np.asarray(contexts[lo:hi], dtype=np.int64)
+        m = np.nonzero((c[:, 0] == v) | (c[:, 2] == v))[0]
+        if len(m) > L:
+            with np.errstate(over="ignore"):
+                base = _mix64(np.array([np.uint64(seed) ^ (np.uint64(item) * np.uint64(0xD1B54A32D192ED03) & _M64) ^
+                                        (np.uint64(v) * np.uint64(0x9E3779B97F4A7C15) & _M64)], dtype=np.uint64))[0]
+                k = (_mix64(base ^ (m.astype(np.uint64) * np.uint64(0x8CB92BA72F3D8DD7) & _M64)) >> np.uint64(32)).astype(np.uint32)
+            m = np.sort(m[np.lexsort((m, k))[:L]])
+        c = c[m]
+        s, p, e = c[:, 0].copy(), c[:, 1], c[:, 2].copy()
+        if shuffle_variable_indexes and var is not None and len(var) > 1:
+            sigma = var_permutation(seed, item, len(var))
+            mp = {int(var[i]): int(var[sigma[i]]) for i in range(len(var))}
+            s = np.asarray([question_token if t == v else mp.get(int(t), int(t)) for t in s], dtype=np.int64)
+            e = np.asarray([question_token if t == v else mp.get(int(t), int(t)) for t in e], dtype=np.int64)
+        else:
+            s[s == v] = question_token
+            e[e == v] = question_token
+        out[0, b, :len(m)] = s; out[1, b, :len(m)] = p; out[2, b, :len(m)] = e
+    return out[0], out[1], out[2]

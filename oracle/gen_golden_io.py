@@ -109,7 +109,7 @@ def builder_vars():
             random.seed(5)
             r = DatasetReader(cp, pp, tp, infer_method=False, infer_variable=True, shuffle_variable_indexes=False)
             o = gg.option(r.terminal_vocab.len(), r.path_vocab.len(), r.label_vocab.len(), 8, 8, 8)
-            o.max_path_length, o.eval_method, o.batch_size = (20 if tag == "synth" else 200), "exact", 32
+            o.max_path_length, o.eval_method, o.batch_size = (5 if tag == "synth" else 200), "exact", 32
             items = list(r.items)
             if tag == "real":
                 items = sorted(items, key=lambda it: -len(it.path_contexts))[:8] + items[100:140]

@@ -88,3 +88,50 @@ def test_epoch_covers_every_method_once_and_shards_by_rank():
     a = [lab for *_, lab in c.epoch(16, 200, 3, rank=0, world=2)]
     b = [lab for *_, lab in c.epoch(16, 200, 3, rank=1, world=2)]
     assert sum(x.numel() for x in a) + sum(x.numel() for x in b) == c.n_items
+
+
+# ---- variable-name task (dataset_builder.py:152-204): c2v_build_batch_vars vs the oracle, bit for bit ---------------
+GV = np.load(os.path.join(ROOT, "tests", "golden", "builder_vars.npz"))
+
+
+def _var_corpus(tag, shuffle):
+    from code2vec_b200.batch_builder import DeviceCorpus
+    units = GV[f"{tag}_units"]
+    T = int(max(GV[f"{tag}_contexts"][:, [0, 2]].max(), GV[f"{tag}_variable_indexes"].max())) + 1
+    c = DeviceCorpus(GV[f"{tag}_offsets"], GV[f"{tag}_contexts"], None, -1, int(GV[f"{tag}_question"]), "cuda:0")
+    c.set_variable_units(units[:, 0], units[:, 1], units[:, 2], GV[f"{tag}_variable_indexes"], T, shuffle)
+    return c, units
+
+
+@pytest.mark.parametrize("tag", ["synth", "real"])
+@pytest.mark.parametrize("shuffle", [False, True])
+@pytest.mark.parametrize("L", [200, 5, 1])
+def test_variable_task_kernel_equals_oracle(tag, shuffle, L):
+    from oracle import batch_oracle as bo
+    c, units = _var_corpus(tag, shuffle)
+    ids = np.concatenate([np.arange(len(units)), np.array([0, len(units) - 1])])
+    for seed in (3, 98765432123456789):
+        s, p, e, lab = c.build_vars(torch.from_numpy(ids), L, seed)
+        rs, rp, re = bo.build_batch_vars(GV[f"{tag}_offsets"], GV[f"{tag}_contexts"], units[:, 0], units[:, 1], ids, L, seed,
+                                         int(GV[f"{tag}_question"]), GV[f"{tag}_variable_indexes"], shuffle)
+        assert np.array_equal(s.cpu().numpy(), rs) and np.array_equal(p.cpu().numpy(), rp) and np.array_equal(e.cpu().numpy(), re)
+        assert np.array_equal(lab.cpu().numpy(), units[ids, 2])
+
+
+def test_variable_task_matches_the_reference_builder_where_the_shuffle_cannot_matter():
+    """bags with <= max_path_length matching contexts: the same multiset as DatasetBuilder.build_data produced"""
+    from collections import Counter
+    c, units = _var_corpus("real", False)
+    L = int(GV["real_L"])
+    s, p, e, lab = c.build_vars(torch.arange(len(units)), L, 1)
+    s, p, e = s.cpu().numpy(), p.cpu().numpy(), e.cpu().numpy()
+    assert np.array_equal(lab.cpu().numpy(), GV["real_ref_label"])
+    same = 0
+    for u in range(len(units)):
+        n = int((GV["real_ref_paths"][u] != 0).sum())
+        if n < L:
+            ref = Counter(map(tuple, np.stack([GV["real_ref_starts"][u, :n], GV["real_ref_paths"][u, :n], GV["real_ref_ends"][u, :n]], 1).tolist()))
+            got = Counter(map(tuple, np.stack([s[u, :n], p[u, :n], e[u, :n]], 1).tolist()))
+            assert ref == got and (p[u, n:] == 0).all()
+            same += 1
+    assert same > 100

@@ -75,3 +75,62 @@ def test_different_seeds_and_items_give_different_bags():
     c = bo.select(1, i + 1, int(OFF[i + 1] - OFF[i]), L)
     assert not np.array_equal(a, b) and not np.array_equal(a, c)
     assert np.array_equal(a, bo.select(1, i, int(OFF[i + 1] - OFF[i]), L))
+
+
+# ---- variable-name task (dataset_builder.py:152-204) pinned to tests/golden/builder_vars.npz ------------------------
+GV = np.load(os.path.join(ROOT, "tests", "golden", "builder_vars.npz"))
+
+
+def _triples(s, p, e):
+    n = int(max((s != 0).sum(), (p != 0).sum(), (e != 0).sum()))
+    return Counter(map(tuple, np.stack([s[:n], p[:n], e[:n]], 1).tolist())), n
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("tag", ["synth", "real"])
+def test_variable_task_oracle_against_the_reference_builder(tag):
+    off, ctx, units = GV[f"{tag}_offsets"], GV[f"{tag}_contexts"], GV[f"{tag}_units"]
+    Lv, q = int(GV[f"{tag}_L"]), int(GV[f"{tag}_question"])
+    rs, rp, re_, rl = (GV[f"{tag}_ref_{k}"] for k in ("starts", "paths", "ends", "label"))
+    assert len(units) == len(rs) and (units[:, 2] == rl).all()            # one bag per (item, @var alias), same order
+    assert (GV[f"{tag}_item_ids"][units[:, 0]] == GV[f"{tag}_ref_ids"]).all()
+    s, p, e = bo.build_batch_vars(off, ctx, units[:, 0], units[:, 1], np.arange(len(units)), Lv, 99, q)
+    n_long = 0
+    for u, (item, v, _) in enumerate(units):
+        c = ctx[off[item]:off[item + 1]].astype(np.int64)
+        c = c[(c[:, 0] == v) | (c[:, 2] == v)].copy()
+        c[c[:, 0] == v, 0] = q; c[c[:, 2] == v, 2] = q
+        pool = Counter(map(tuple, c.tolist()))
+        mine, n_mine = _triples(s[u], p[u], e[u])
+        ref, n_ref = _triples(rs[u], rp[u], re_[u])
+        assert n_mine == n_ref == min(len(c), Lv)
+        assert not (mine - pool) and not (ref - pool)
+        assert (s[u, n_mine:] == 0).all() and (p[u, n_mine:] == 0).all() and (e[u, n_mine:] == 0).all()
+        assert v not in s[u] and v not in e[u]
+        if len(c) <= Lv:
+            assert mine == ref                                                # the shuffle cannot change the content
+        else:
+            n_long += 1
+    assert n_long >= 1
+
+
+def test_variable_permutation_is_a_permutation_and_only_touches_variables():
+    off, ctx, units = GV["synth_offsets"], GV["synth_contexts"], GV["synth_units"]
+    var = GV["synth_variable_indexes"]
+    Lv, q = int(GV["synth_L"]), int(GV["synth_question"])
+    ids = np.arange(len(units))
+    s0, p0, e0 = bo.build_batch_vars(off, ctx, units[:, 0], units[:, 1], ids, Lv, 7, q)
+    s1, p1, e1 = bo.build_batch_vars(off, ctx, units[:, 0], units[:, 1], ids, Lv, 7, q, var, True)
+    assert (p0 == p1).all()
+    changed = 0
+    for u, (item, v, _) in enumerate(units):
+        sigma = bo.var_permutation(7, int(item), len(var))
+        assert sorted(sigma.tolist()) == list(range(len(var)))
+        mp = {int(var[i]): int(var[sigma[i]]) for i in range(len(var))}
+        for a0, a1 in ((s0[u], s1[u]), (e0[u], e1[u])):
+            want = np.asarray([t if t == q or t == 0 else mp.get(int(t), int(t)) for t in a0])
+            assert (want == a1).all()
+            changed += int((a0 != a1).sum())
+    assert changed > 0
