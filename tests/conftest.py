@@ -15,7 +15,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
 
 
-def golden_names(prefix=None, exclude_prefix=("init_", "builder_")):
+def golden_names(prefix=None, exclude_prefix=("init_", "builder_", "reader_", "writer")):
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
     names = [n for n in names if not n.startswith(tuple(exclude_prefix))]
     if prefix is not None:
