@@ -7,6 +7,8 @@
 // Same operation order as torch's single-tensor Adam (amsgrad=False, maximize=False):
 //   g += wd * p;  m += (g - m) * (1 - b1);  v = v * b2 + (1 - b2) * g * g;
 //   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+#include <cstring>
+
 #include "c2v_common.cuh"
 
 namespace c2v {
@@ -39,6 +41,70 @@ adam_step_kernel(float4 *__restrict__ p, float4 *__restrict__ g, float4 *__restr
         pt[i] = P; mt[i] = M; vt[i] = V;
         if (zero_grad) gt[i] = G;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sharded step over NVLink (data-parallel training, SURVEY.md 8e + section 5 "later option"): ONE kernel per rank does
+// the gradient reduction, the optimizer and the parameter broadcast for the rank's 1/world slice of the flat buffers:
+//   g  = sum over ranks of grad[slice]      multimem.ld_reduce.add.f32 through the NVSwitch multicast mapping
+//                                           (in-switch reduction, NVLS) or fixed-order loads from the peers' buffers
+//   Adam on (p, m, v)[slice]                m, v exist only on the owner of the slice (1/world of the optimizer state)
+//   p' -> every rank's parameter buffer     multimem.st (one store, the switch replicates it) or world peer stores
+// and, while the NVLink traffic is in flight, zeroes the rank's OTHER gradient bucket (the buckets alternate between
+// steps: peers may still be reading this step's bucket, nobody reads the other one).  The caller brackets the launch
+// with two cross-GPU barriers (all gradients complete before / all parameter stores landed after).
+// ------------------------------------------------------------------------------------------------------------------
+struct AdamPeers { float *param[16]; const float *grad[16]; };
+
+__device__ __forceinline__ float4 mm_ld_reduce_add(const float *mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mm_st(float *mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <bool MULTIMEM>
+__global__ void __launch_bounds__(256)
+adam_step_sharded_kernel(const float *__restrict__ p_local, float *__restrict__ p_mc, const float *__restrict__ g_mc,
+                         const AdamPeers peers, int world, float4 *__restrict__ m, float4 *__restrict__ v,
+                         long long slice_begin, long long slice_n4, float4 *__restrict__ zero_buf, long long zero_n4,
+                         float step_size, float one_minus_b1, float b2, float one_minus_b2, float inv_sqrt_bc2, float eps,
+                         float wd, float gscale)
+{
+    auto upd = [&](float &pp, float gg, float &mm, float &vv) {
+        float gr = gg * gscale;
+        if (wd != 0.0f) gr = fmaf(wd, pp, gr);
+        mm = mm + (gr - mm) * one_minus_b1;
+        vv = vv * b2 + one_minus_b2 * gr * gr;
+        const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+        pp = pp - step_size * (mm / denom);
+    };
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = t0; i < slice_n4; i += stride) {
+        const long long e = slice_begin + 4 * i;               // element offset in the flat buffers
+        float4 G;
+        if (MULTIMEM) G = mm_ld_reduce_add(g_mc + e);
+        else {
+            G = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < world; ++r) {                   // fixed rank order: every replica of the sum is bit-identical
+                const float4 x = *reinterpret_cast<const float4 *>(peers.grad[r] + e);
+                G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
+            }
+        }
+        float4 P = *reinterpret_cast<const float4 *>(p_local + e), M = m[i], V = v[i];
+        upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+        m[i] = M; v[i] = V;
+        if (MULTIMEM) mm_st(p_mc + e, P);
+        else
+            for (int r = 0; r < world; ++r) *reinterpret_cast<float4 *>(peers.param[r] + e) = P;
+    }
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = t0; i < zero_n4; i += stride) zero_buf[i] = z;      // next step's gradient bucket (local HBM only)
+    __threadfence_system();
 }
 
 }  // namespace c2v
@@ -74,5 +140,62 @@ extern "C" int c2v_adam_step(float *param, float *grad, float *exp_avg, float *e
         reinterpret_cast<float4 *>(exp_avg_sq), n4, param + n4 * 4, grad + n4 * 4, exp_avg + n4 * 4, exp_avg_sq + n4 * 4, tail,
         step_size, 1.0f - beta1, beta2, 1.0f - beta2, inv_sqrt_bc2, eps, weight_decay, grad_scale, zero_grad);
     C2V_LAUNCH_OK("adam_step_kernel");
+    return C2V_OK;
+}
+
+extern "C" int c2v_adam_step_sharded(const float *param_local, float *param_multicast, const float *grad_multicast,
+                                     float *const *param_peers, const float *const *grad_peers, int32_t world,
+                                     float *exp_avg_slice, float *exp_avg_sq_slice, int64_t slice_begin, int64_t slice_n,
+                                     float *zero_buffer, int64_t zero_n, float lr, float beta1, float beta2, float eps,
+                                     float weight_decay, int64_t step, float grad_scale, void *stream)
+{
+    if (!param_local || !exp_avg_slice || !exp_avg_sq_slice || slice_n < 0 || slice_begin < 0 || step < 1 || world < 1 ||
+        world > 16) {
+        set_error("c2v_adam_step_sharded: bad argument");
+        return C2V_EINVAL;
+    }
+    const bool mm = param_multicast != nullptr && grad_multicast != nullptr;
+    if (!mm && (!param_peers || !grad_peers)) {
+        set_error("c2v_adam_step_sharded: needs either the multicast pointers or the peer pointer tables");
+        return C2V_EINVAL;
+    }
+    if ((slice_begin | slice_n | zero_n) & 3) {
+        set_error("c2v_adam_step_sharded: slice_begin, slice_n and zero_n must be multiples of 4 elements");
+        return C2V_EINVAL;
+    }
+    AdamPeers peers;
+    memset(&peers, 0, sizeof(peers));
+    uintptr_t align = reinterpret_cast<uintptr_t>(param_local) | reinterpret_cast<uintptr_t>(exp_avg_slice) |
+                      reinterpret_cast<uintptr_t>(exp_avg_sq_slice) | reinterpret_cast<uintptr_t>(zero_buffer) |
+                      reinterpret_cast<uintptr_t>(param_multicast) | reinterpret_cast<uintptr_t>(grad_multicast);
+    if (!mm)
+        for (int r = 0; r < world; ++r) {
+            if (!param_peers[r] || !grad_peers[r]) { set_error("c2v_adam_step_sharded: NULL peer pointer %d", r); return C2V_EINVAL; }
+            peers.param[r] = param_peers[r]; peers.grad[r] = grad_peers[r];
+            align |= reinterpret_cast<uintptr_t>(param_peers[r]) | reinterpret_cast<uintptr_t>(grad_peers[r]);
+        }
+    if (align & 15) { set_error("c2v_adam_step_sharded: buffers must be 16-byte aligned"); return C2V_EINVAL; }
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    int dev = 0, sms = 0;
+    C2V_CUDA_OK(cudaGetDevice(&dev));
+    C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long n4 = slice_n / 4, z4 = zero_buffer ? zero_n / 4 : 0;
+    long long blocks = ((n4 > z4 ? n4 : z4) + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    if (blocks < 1) blocks = 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mm)
+        adam_step_sharded_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(
+            param_local, param_multicast, grad_multicast, peers, world, reinterpret_cast<float4 *>(exp_avg_slice),
+            reinterpret_cast<float4 *>(exp_avg_sq_slice), slice_begin, n4, reinterpret_cast<float4 *>(zero_buffer), z4,
+            step_size, 1.0f - beta1, beta2, 1.0f - beta2, inv_sqrt_bc2, eps, weight_decay, grad_scale);
+    else
+        adam_step_sharded_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(
+            param_local, param_multicast, grad_multicast, peers, world, reinterpret_cast<float4 *>(exp_avg_slice),
+            reinterpret_cast<float4 *>(exp_avg_sq_slice), slice_begin, n4, reinterpret_cast<float4 *>(zero_buffer), z4,
+            step_size, 1.0f - beta1, beta2, 1.0f - beta2, inv_sqrt_bc2, eps, weight_decay, grad_scale);
+    C2V_LAUNCH_OK("adam_step_sharded_kernel");
     return C2V_OK;
 }

@@ -115,8 +115,175 @@ class FlatAdam:
         self.bucket.zero()
 
 
+class ShardedFlatAdam:
+    """Data-parallel Adam with the optimizer state sharded over the ranks and the gradient reduction fused into the
+    optimizer kernel (SURVEY.md section 5 "later option").  Same update rule, dense, as
+    torch.optim.Adam (main.py:138) -- every rank ends a step with bit-identical parameters.
+
+    Layout: parameters live in ONE flat fp32 buffer (views, like FlatAdam), gradients in TWO flat buckets that alternate
+    between steps (`.grad` of every parameter is re-pointed after each step); the flat length is padded to a multiple of
+    4 * world and rank r owns slice r (exp_avg / exp_avg_sq exist only for the owned slice: 1/world of the state).
+
+    transport
+      "nvls"  buffers are symmetric memory (torch.distributed._symmetric_memory: plumbing only -- allocation, the
+              multicast mapping, the cross-GPU barriers); one `c2v_adam_step_sharded` launch per rank reduces the slice's
+              gradients in the NVSwitch (`multimem.ld_reduce`), runs Adam, and multicasts the new parameters
+              (`multimem.st`), zero-filling the other bucket meanwhile.  No NCCL call in the step.
+      "p2p"   same kernel, peer pointers instead of the multicast mapping (NVLink loads / stores, rank-ordered sum).
+      "nccl"  reduce_scatter -> `c2v_adam_step` on the slice -> all_gather (two NCCL collectives; the fallback when
+              symmetric memory is unavailable, and what the gloo CPU tests drive with a stand-in kernel).
+      "auto"  nvls if the group has multicast support, else p2p if symmetric memory works, else nccl.
+    """
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None, transport="auto"):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        dev, dt = self.params[0].device, self.params[0].dtype
+        if dt != torch.float32:
+            raise TypeError("parameters must be fp32")
+        self.numel = sum(p.numel() for p in self.params)
+        q = 4 * self.world
+        self.padded = (self.numel + q - 1) // q * q
+        self.slice_n = self.padded // self.world
+        self.slice_begin = self.rank * self.slice_n
+        self.transport, self._hdl = self._allocate(transport, dev)
+        o = 0
+        self._grad_views = ([], [])
+        for p in self.params:
+            if p.device != dev or p.dtype != dt:
+                raise ValueError("parameters must share device and dtype")
+            n = p.numel()
+            self.flat_param[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[o:o + n].view_as(p)
+            for k in (0, 1):
+                self._grad_views[k].append(self.buckets[k][o:o + n].view_as(p))
+            o += n
+        self.flat_param[self.numel:].zero_()
+        self.exp_avg = torch.zeros(self.slice_n, dtype=dt, device=dev)
+        self.exp_avg_sq = torch.zeros(self.slice_n, dtype=dt, device=dev)
+        self.t, self.cur = 0, 0
+        self._point_grads(0)
+        if self.world > 1:
+            dist.barrier(group)
+
+    # ---- buffers ------------------------------------------------------------------------------------------------------
+    def _allocate(self, transport, dev):
+        n = self.padded
+        want = transport
+        if self.world > 1 and want in ("auto", "nvls", "p2p") and dev.type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                g = self.group if self.group is not None else dist.group.WORLD
+                bufs = [symm.empty(n, dtype=torch.float32, device=dev) for _ in range(3)]
+                hdls = [symm.rendezvous(b, g) for b in bufs]
+                for b in bufs:
+                    b.zero_()
+                self.flat_param, self.buckets = bufs[0], (bufs[1], bufs[2])
+                mc = all(int(h.multicast_ptr) != 0 for h in hdls)
+                if want == "nvls" and not mc:
+                    raise RuntimeError("this process group has no NVSwitch multicast support")
+                return ("nvls" if (mc and want != "p2p") else "p2p"), hdls
+            except Exception:
+                if want in ("nvls", "p2p"):
+                    raise
+        if want in ("nvls", "p2p") and self.world > 1:
+            raise RuntimeError(f"transport {want!r} needs CUDA symmetric memory")
+        self.flat_param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.buckets = (torch.zeros(n, dtype=torch.float32, device=dev), torch.zeros(n, dtype=torch.float32, device=dev))
+        return "nccl", None
+
+    def _point_grads(self, k):
+        for p, v in zip(self.params, self._grad_views[k]):
+            p.grad = v
+        self.cur = k
+
+    @property
+    def bucket(self):
+        """the flat gradient bucket the next backward accumulates into"""
+        return self.buckets[self.cur]
+
+    def state_bytes(self):
+        return 4 * (2 * self.slice_n)
+
+    def zero_grad(self):
+        self.buckets[self.cur].zero_()
+
+    # ---- the step -----------------------------------------------------------------------------------------------------
+    def _adam_slice(self, p_slice, g_slice):
+        """c2v_adam_step on the owned slice (the gloo CPU tests replace this method with a torch stand-in)"""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        dev = p_slice.device
+        with torch.cuda.device(dev):
+            rc = lib.c2v_adam_step(P(p_slice), P(g_slice), P(self.exp_avg), P(self.exp_avg_sq), p_slice.numel(), self.lr,
+                                   self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, 1.0 / self.world, 0,
+                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "c2v_adam_step")
+
+    def _reduce_scatter(self, out, full):
+        try:
+            dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.group)
+        except (RuntimeError, NotImplementedError):          # gloo (CPU tests) has no reduce_scatter
+            tmp = full.clone()
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
+            out.copy_(tmp[self.slice_begin:self.slice_begin + self.slice_n])
+
+    def step(self):
+        """reduce this step's gradients over the ranks (mean), Adam, parameters identical everywhere afterwards; the
+        other bucket is left zeroed and becomes the target of the next backward (main.py:171 + :175)."""
+        import ctypes
+        self.t += 1
+        cur, nxt = self.cur, 1 - self.cur
+        lo, hi = self.slice_begin, self.slice_begin + self.slice_n
+        if self.world == 1 or self.transport == "nccl":
+            if self.world > 1:
+                g_slice = torch.empty(self.slice_n, dtype=torch.float32, device=self.flat_param.device)
+                self._reduce_scatter(g_slice, self.buckets[cur])
+            else:
+                g_slice = self.buckets[cur][lo:hi]
+            self._adam_slice(self.flat_param[lo:hi], g_slice)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.flat_param, self.flat_param[lo:hi].clone(), group=self.group)
+            self.buckets[nxt].zero_()
+        else:
+            from . import _lib
+            lib = _lib.load()
+            hp, hg = self._hdl[0], self._hdl[1 + cur]
+            dev = self.flat_param.device
+            V = ctypes.c_void_p
+            use_mc = self.transport == "nvls"
+            pp = (V * self.world)(*[int(x) for x in hp.buffer_ptrs])
+            gp = (V * self.world)(*[int(x) for x in hg.buffer_ptrs])
+            with torch.cuda.device(dev):
+                hg.barrier(channel=0)                            # every rank's backward has finished writing its bucket
+                rc = lib.c2v_adam_step_sharded(
+                    V(self.flat_param.data_ptr()), V(int(hp.multicast_ptr)) if use_mc else None,
+                    V(int(hg.multicast_ptr)) if use_mc else None, pp, gp, self.world, V(self.exp_avg.data_ptr()),
+                    V(self.exp_avg_sq.data_ptr()), lo, self.slice_n, V(self.buckets[nxt].data_ptr()), self.padded, self.lr,
+                    self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, 1.0 / self.world,
+                    V(torch.cuda.current_stream(dev).cuda_stream))
+                _lib.check(rc, "c2v_adam_step_sharded")
+                hp.barrier(channel=1)                            # every rank's parameter stores have landed here
+        self._point_grads(nxt)
+        for p in self.params:                                    # raw-pointer writes: bump the version counters
+            torch.autograd.graph.increment_version(p)
+
+
 def ddp_step(model, optimizer, bucket, starts, paths, ends, label, loss_fn):
     """One training step of main.py:171-175 on this rank's shard of the global batch."""
+    if isinstance(optimizer, ShardedFlatAdam):               # reduction + optimizer + broadcast are one kernel per rank
+        outputs, code_vector, attention = model.forward(starts, paths, ends, label)
+        loss = loss_fn(outputs, label)
+        loss.backward()
+        optimizer.step()
+        return loss
     fused = isinstance(optimizer, FlatAdam)
     if not fused:
         bucket.zero()                       # (FlatAdam leaves the bucket zeroed at the end of its step)

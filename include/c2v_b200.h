@@ -259,6 +259,21 @@ int c2v_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, 
                   float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                   int32_t zero_grad, void *stream);
 
+/* The same optimizer for data-parallel training, fused with its collective ("one all_reduce per step"
+ * becomes one kernel per rank): for the rank's slice [slice_begin, slice_begin + slice_n) of the flat buffers the kernel
+ * (1) sums the gradients of all ranks -- `multimem.ld_reduce` on grad_multicast (NVSwitch in-switch reduction) or, when
+ * the multicast pointers are NULL, loads from grad_peers[0..world) in rank order over NVLink peer mappings --, (2) runs
+ * Adam on param_local[slice] with exp_avg_slice / exp_avg_sq_slice (optimizer state is sharded: slice_n elements),
+ * (3) stores the new parameters into every rank's buffer (`multimem.st` on param_multicast, or param_peers[r]), and
+ * (4) zero-fills zero_buffer[0..zero_n) (the rank's other gradient bucket) while the links are busy.  param_peers /
+ * grad_peers are HOST arrays of `world` device pointers.  slice_begin, slice_n, zero_n: multiples of 4 elements.
+ * The caller provides the two cross-GPU barriers around the launch (all gradients complete / all stores landed). */
+int c2v_adam_step_sharded(const float *param_local, float *param_multicast, const float *grad_multicast,
+                          float *const *param_peers, const float *const *grad_peers, int32_t world,
+                          float *exp_avg_slice, float *exp_avg_sq_slice, int64_t slice_begin, int64_t slice_n,
+                          float *zero_buffer, int64_t zero_n, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int64_t step, float grad_scale, void *stream);
+
 /* ---- corpus reader / code-vector writer: the data formats either side of the path ----------
  * c2v_corpus_parse_*: DatasetReader.load (/root/reference/model/dataset_reader.py:72-128) for the `corpus.txt` format
  * (`#id`, `label:`, `class:`, `paths:` + `start\tpath\tend` lines, `vars:` + `original\talias` lines, blank line between
