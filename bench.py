@@ -160,13 +160,38 @@ def synth_pool(w, n_batches, device, seed):
     return mk(w["T"]), mk(w["P"]), mk(w["T"]), torch.randint(0, w["C"], (n,), generator=g, device=device, dtype=torch.int64)
 
 
+def bench_config(w, args):
+    """the `config` object of the JSON line -- ONE function for both arms, so the driver's same_config check holds"""
+    nb = args.pool_batches
+    return {"workload": w["name"], "detail": w["desc"], "batch_per_gpu": w["B"], "bag": w["L"],
+            "step": "Code2Vec.forward: encode + finalize + label logits + argmax",
+            "sharding": "methods sharded by rank, parameters replicated, no collective in forward",
+            "l2": f"inputs larger than L2: {(w['T'] * w['Et'] + w['P'] * w['Ep']) * 4 / 1e6:.0f} MB of tables, "
+                  f"{nb} distinct batches ({nb * w['B'] * w['L'] * 24 / 1e6:.0f} MB of indices) cycled"}
+
+
+def find_reference_module():
+    """The UNMODIFIED reference `model.model.Code2Vec` if it can be imported on this box: baseline/_ref first, then
+    /root/reference.  The reference has neither setup.py nor pyproject.toml, so the offline pip
+    install into baseline/_ref fails ("not installable") and the GPU box has neither path: -> None there."""
+    for root in (os.path.join(ROOT, "baseline", "_ref"), os.environ.get("C2V_REFERENCE", "/root/reference")):
+        if os.path.exists(os.path.join(root, "model", "model.py")):
+            try:
+                sys.dont_write_bytecode = True
+                sys.path.insert(0, root)
+                from model.model import Code2Vec as RefCode2Vec          # noqa: the reference, unmodified
+                return RefCode2Vec, root
+            except Exception:
+                sys.path.remove(root)
+    return None, None
+
+
 def run_reference(args, w):
-    """The reference's own CPU implementation of the path, timed on this box's host cores.
-    The reference is pure PyTorch and cannot travel to the GPU box (no pip-installable package,
-    /root/reference absent there), so this runs oracle.torch_forward: the same ATen CPU ops
-    in the same order (pinned to the reference by tests/test_oracle_golden.py)."""
+    """The reference's own CPU implementation of the path, timed on this box's host cores: the unmodified
+    /root/reference/model/model.py when this box has it (kind "reference"), else oracle.torch_forward, the same ATen CPU
+    ops in the same order, pinned to the reference by tests/test_oracle_golden.py (kind "port")."""
+    import types
     import torch
-    from oracle import oracle
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -175,16 +200,33 @@ def run_reference(args, w):
     p = synth_params(w, dev)
     s, pth, e, lab = synth_pool(w, 2, dev, 1234)
     B, L = w["B"], w["L"]
-    # all the host threads it can use: pick the fastest of {all, 1/2, 1/4, 16} on one probe batch
+    RefCode2Vec, ref_root = find_reference_module()
+    if RefCode2Vec is not None:
+        o = types.SimpleNamespace(terminal_count=w["T"], path_count=w["P"], label_count=w["C"], terminal_embed_size=w["Et"],
+                                  path_embed_size=w["Ep"], encode_size=w["H"], dropout_prob=0.25, angular_margin_loss=False,
+                                  angular_margin=0.5, inverse_temp=30.0, device=dev)
+        ref = RefCode2Vec(o)
+        ref.load_state_dict(p)
+        ref.eval()
+        fwd = lambda a, b, c, d: ref.forward(a, b, c, d)
+        kind, how = "reference", f"unmodified {ref_root}/model/model.py Code2Vec.forward (eval, no_grad)"
+    else:
+        from oracle import oracle
+        fwd = lambda a, b, c, d: oracle.torch_forward(p, a, b, c, d)
+        kind, how = "port", "torch-CPU restatement (oracle.torch_forward; the reference is not installable and absent on this box)"
+    # all the host threads it can use: the fastest of {all, 1/2, 1/4, 16} threads, each judged by the best of 3 passes
     best_nt, best_t = cores, None
     for nt in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16)}, reverse=True):
         torch.set_num_threads(nt)
         with torch.no_grad():
-            oracle.torch_forward(p, s[:B], pth[:B], e[:B], lab[:B])
-            t0 = time.perf_counter()
-            oracle.torch_forward(p, s[:B], pth[:B], e[:B], lab[:B])
-            dtp = time.perf_counter() - t0
-        if best_t is None or dtp < best_t:
+            fwd(s[:B], pth[:B], e[:B], lab[:B])
+            dtp = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                fwd(s[:B], pth[:B], e[:B], lab[:B])
+                d1 = time.perf_counter() - t0
+                dtp = d1 if dtp is None else min(dtp, d1)
+        if best_t is None or dtp < best_t * 0.97:             # prefer more threads unless clearly slower
             best_nt, best_t = nt, dtp
     torch.set_num_threads(best_nt)
     cores_used = best_nt
@@ -192,7 +234,7 @@ def run_reference(args, w):
     def step(i):
         o = (i % 2) * B
         with torch.no_grad():
-            out, cv, att = oracle.torch_forward(p, s[o:o + B], pth[o:o + B], e[o:o + B], lab[o:o + B])
+            out, cv, att = fwd(s[o:o + B], pth[o:o + B], e[o:o + B], lab[o:o + B])
             return out.max(dim=1)
     for i in range(args.warmup):
         step(i)
@@ -205,10 +247,9 @@ def run_reference(args, w):
         "impl": "reference", "metric": "path-contexts/sec", "value": val, "unit": "ctx/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["name"], "detail": w["desc"], "batch": B, "bag": L},
-        "cpu_baseline": {"value": val, "unit": "ctx/s", "cores": cores_used, "host_cores": cores, "kind": "port",
-                         "sample": f"{args.steps} forward passes of one {B}x{L} batch, torch-CPU restatement "
-                                   f"(oracle.torch_forward), {torch.get_num_threads()} threads"},
+        "config": bench_config(w, args),
+        "cpu_baseline": {"value": val, "unit": "ctx/s", "cores": cores_used, "host_cores": cores, "kind": kind,
+                         "sample": f"{args.steps} forward passes of {B}x{L} batches, {how}, {torch.get_num_threads()} threads"},
         "e2e": {"value": val, "unit": "ctx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -225,6 +266,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--train-steps", type=int, default=8, help="also time K training steps (0 = skip)")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the ATen/cuBLAS eager comparator on this GPU")
+    ap.add_argument("--transport", default="auto", choices=["auto", "nvls", "p2p", "nccl"],
+                    help="gradient reduction of the training leg (ShardedFlatAdam)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload]); w["name"] = args.workload
 
@@ -313,33 +357,48 @@ def main():
         parity["ok"] = max(parity["max_abs_err"].values()) <= 1e-4
 
     # ---- device-resident throughput ("value") --------------------------------------------------
+    # The driver runs --steps 20: one pass of K steps lasts ~2 ms, too short for clocks sampling or kernel statistics.
+    # The K-step pass (barrier + synchronize on both sides, CUDA events around exactly K steps) is therefore REPEATED
+    # until >= MIN_REGION_S of GPU time has been measured; the reported ms_per_step is the MEDIAN pass.
+    MIN_REGION_S = 0.6
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
+
+    def timed_pass(first):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for i in range(args.steps):
+            step(first + i)
+        ev1.record(stream)
+        barrier()
+        return ev0.elapsed_time(ev1)
+
+    probe = timed_pass(args.warmup)                            # untimed: sizes the repetition count
+    tp = torch.tensor([probe], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    reps = int(min(2000, max(3, -(-MIN_REGION_S * 1e3 // max(float(tp.item()), 1e-3)))))
     sampler.mark_begin()
     lib.c2v_profile_enable(8)              # CUDA events around the dominant kernel on every 8th step of the timed loop
     l0 = lib.c2v_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for i in range(args.steps):
-        step(args.warmup + i)
-    ev1.record(stream)
-    barrier()
+    t_wall0 = time.perf_counter()
+    pass_ms = [timed_pass(args.warmup + (r + 1) * args.steps) for r in range(reps)]
+    timed_region_s = time.perf_counter() - t_wall0
     sampler.mark_end()
-    ms = ev0.elapsed_time(ev1)
-    launches = lib.c2v_launch_count() - l0
+    launches = (lib.c2v_launch_count() - l0) / reps           # per K-step pass
     kms, kcnt = ctypes.c_double(0), ctypes.c_int64(0)
     lib.c2v_profile_read(ctypes.byref(kms), ctypes.byref(kcnt))
     lib.c2v_profile_enable(0)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    t = torch.tensor(pass_ms, dtype=torch.float64, device=dev)
     lt = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-    ms_max = float(t.item())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(lt, op=dist.ReduceOp.SUM)   # per pass: max over ranks
+    ms_max = float(t.median().item())
     value = world * B * L * args.steps / (ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel (this rank) -----------------------------------------------
@@ -350,20 +409,55 @@ def main():
     kvar = {"ldg": "encode_tcgen05_kernel", "tma": "encode_tma_kernel", "cpa": "encode_cpa_kernel"}.get(
         os.environ.get("C2V_ENCODE_KERNEL", ""), "encode_tm_kernel")
     traffic = None
-    try:      # DRAM traffic of the dominant kernel from the committed ncu capture (same workload), per launch
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        if tj["kernel"] == kvar and args.workload == "cfg2":
-            traffic = tj["traffic_bytes_per_launch"]
-    except Exception:
-        pass
+    for tf in ("r2_traffic.json", "r1_traffic.json"):   # DRAM traffic of the dominant kernel from the committed ncu capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", tf)))
+            if tj["kernel"] == kvar and tj.get("workload", "cfg2") == args.workload:
+                traffic = tj["traffic_bytes_per_launch"]
+                break
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": kvar if lib.c2v_encode_supports_tcgen05(ctypes.byref(dims)) and algo != _lib.ALGO_FFMA else "encode_ffma_kernel",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "ctx_per_s_kernel_only": B * L / (k_ms * 1e-3) if k_ms > 0 else 0.0}
+                "kernel_ms": k_ms, "kernel_samples": int(kcnt.value), "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": peak_src, "ctx_per_s_kernel_only": B * L / (k_ms * 1e-3) if k_ms > 0 else 0.0,
+                "how": "CUDA events on the launch stream around every 8th launch of the kernel inside the timed passes "
+                       "(launch + prologue inside the interval, no dependent-launch overlap for the bracketed launch)"}
+
+    # ---- the same path on the existing Blackwell kernels: ATen/cuBLAS eager on this GPU ----------
+    gpu_eager = None
+    if rank == 0 and not args.no_gpu_eager:
+        try:
+            from oracle import oracle as _or                 # baseline leg only: the torch restatement dispatches to ATen
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            def estep(i):
+                o = (i % nb) * B
+                with torch.no_grad():
+                    o_, _, _ = _or.torch_forward(p, s[o:o + B], pth[o:o + B], e[o:o + B], lab[o:o + B])
+                    return o_.max(dim=1)
+            for i in range(3):
+                estep(i)
+            torch.cuda.synchronize(dev)
+            n_e = max(5, min(args.steps, 50))
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for i in range(n_e):
+                estep(3 + i)
+            g1.record(stream)
+            torch.cuda.synchronize(dev)
+            gms = g0.elapsed_time(g1) / n_e
+            gpu_eager = {"value": B * L / (gms * 1e-3), "unit": "ctx/s", "ms_per_step": gms, "steps": n_e, "n_gpus": 1,
+                         "what": "the reference's op sequence (model.py:48-83 + torch.max) as eager ATen/cuBLAS kernels on this "
+                                 "B200, fp32, allow_tf32=False (oracle.torch_forward on cuda; the reference itself is absent here)"}
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            gpu_eager = {"value": None, "unit": "ctx/s", "what": f"failed: {type(ex).__name__}: {ex}"}
 
     # ---- end to end through the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside) ------
     e2e = None
     if not args.no_e2e:
+        bound = bind_to_gpu_numa_node(local)             # before the pinned staging buffers and the session exist
         sess = ctypes.c_void_p()
         _lib.check(lib.c2v_session_create(local, ctypes.byref(dims), B, L, ctypes.byref(sess)), "session")
         hb = min(nb, 8)
@@ -387,29 +481,46 @@ def main():
                     _lib.check(lib.c2v_session_wait(sess, pending.pop(0)), "session_wait")
             for tk in pending:
                 _lib.check(lib.c2v_session_wait(sess, tk), "session_wait")
-        host_loop(max(args.warmup, 3))
-        barrier()
-        t0 = time.perf_counter()
-        host_loop(args.steps)
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+
+        def host_pass():
+            barrier()
+            t0 = time.perf_counter()
+            host_loop(args.steps)
+            torch.cuda.synchronize(dev)
+            return time.perf_counter() - t0
+        # warm up until two consecutive passes agree within 5 % (first passes pay page faults / the copy engines' ramp)
+        prev, n_warm = host_pass(), 1
+        while n_warm < 12:
+            cur = host_pass(); n_warm += 1
+            tw = torch.tensor([1.0 if abs(cur - prev) <= 0.05 * prev else 0.0], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tw, op=dist.ReduceOp.MIN)      # every rank takes the same number of passes
+            prev = cur
+            if tw.item() > 0:
+                break
+        te = torch.tensor([prev], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_reps = int(min(400, max(3, -(-MIN_REGION_S // max(float(te.item()), 1e-6)))))
+        te = torch.tensor([host_pass() for _ in range(e_reps)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)           # per pass: the slowest rank
+        dt = float(te.median().item())
         lib.c2v_session_destroy(sess)
-        e2e = {"value": world * B * L * args.steps / float(te.item()), "unit": "ctx/s",
+        e2e = {"value": world * B * L * args.steps / dt, "unit": "ctx/s",
                "h2d_bytes_per_step": 3 * B * L * 8, "d2h_bytes_per_step": B * H * 4 + B * L * 4 + B * 8 + B * 4 + 8,
                "api": "c2v_forward_host_async (4 batches in flight on upload / compute / download streams; pinned host int64 indices in, code_vector + "
-                      "attention + argmax/score out)", "ms_per_step": float(te.item()) / args.steps * 1e3}
+                      "attention + argmax/score out; the [B, C] logits stay on the device: this is the predict surface of main.py:282-285)",
+               "ms_per_step": dt / args.steps * 1e3, "passes": e_reps, "warmup_passes": n_warm, "cpu_binding": bound}
 
-    # ---- training step (reported beside the metric, not the metric): main.py:171-175 on this rank's
-    #      shard + ONE flat-bucket allreduce of the gradients (NCCL over NVLink) + Adam
+    # ---- training step (reported beside the metric, not the metric): main.py:171-175 on this rank's shard; the gradient
+    #      reduction over the ranks is fused into the optimizer kernel (ShardedFlatAdam, NVLS) -- no NCCL call in the step
     train = None
     if args.train_steps > 0:
         import types
         import torch.nn.functional as F
         from code2vec_b200.model import Code2Vec
-        from code2vec_b200.distributed import FlatAdam, FlatGradBucket, ddp_step
+        from code2vec_b200.distributed import ShardedFlatAdam, ddp_step
         opt_ns = types.SimpleNamespace(terminal_count=w["T"], path_count=w["P"], label_count=C,
                                        terminal_embed_size=w["Et"], path_embed_size=w["Ep"], encode_size=H,
                                        dropout_prob=0.25, angular_margin_loss=False, angular_margin=0.5,
@@ -417,29 +528,34 @@ def main():
         model = Code2Vec(opt_ns, algo=args.algo)
         model.load_state_dict(p)
         model = model.to(dev).train()
-        bucket = FlatGradBucket(model.parameters())
-        optim = FlatAdam(bucket, lr=0.01, betas=(0.9, 0.999))      # main.py:138 as one launch (c2v_adam_step; = torch's Adam)
+        optim = ShardedFlatAdam(model.parameters(), lr=0.01, betas=(0.9, 0.999), transport=args.transport)   # main.py:138
         loss_fn = lambda o_, l_: F.nll_loss(F.log_softmax(o_, dim=1), l_)            # main.py:251-264
         def tstep(i):
             o = (i % nb) * B
-            return ddp_step(model, optim, bucket, s[o:o + B], pth[o:o + B], e[o:o + B], lab[o:o + B], loss_fn)
+            return ddp_step(model, optim, None, s[o:o + B], pth[o:o + B], e[o:o + B], lab[o:o + B], loss_fn)
         for i in range(3):
             tstep(i)
         barrier()
-        tv0, tv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tv0.record(stream)
-        for i in range(args.train_steps):
-            last = tstep(3 + i)
-        tv1.record(stream)
-        barrier()
-        tt = torch.tensor([tv0.elapsed_time(tv1)], dtype=torch.float64, device=dev)
+        def train_pass(first):
+            tv0, tv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tv0.record(stream)
+            for i in range(args.train_steps):
+                last = tstep(first + i)
+            tv1.record(stream)
+            barrier()
+            return tv0.elapsed_time(tv1), last
+        t_reps = 5
+        res = [train_pass(3 + r * args.train_steps) for r in range(t_reps)]
+        tt = torch.tensor([r[0] for r in res], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        train = {"value": world * B * L * args.train_steps / (float(tt.item()) * 1e-3), "unit": "ctx/s",
-                 "ms_per_step": float(tt.item()) / args.train_steps, "steps": args.train_steps,
-                 "step": "forward(dropout .25) + mean NLL + backward + 1 allreduce + dense Adam with the zero_grad folded in (c2v_adam_step)",
-                 "allreduce_bytes": bucket.nbytes(), "loss": float(last.item())}
-        del model, optim, bucket
+        tms = float(tt.median().item())
+        train = {"value": world * B * L * args.train_steps / (tms * 1e-3), "unit": "ctx/s",
+                 "ms_per_step": tms / args.train_steps, "steps": args.train_steps, "passes": t_reps,
+                 "step": "forward(dropout .25) + mean NLL + backward + gradient reduction over the ranks + dense Adam "
+                         "(optimizer state sharded 1/world; reduction + Adam + parameter broadcast = one kernel per rank)",
+                 "transport": optim.transport, "gradient_bytes": 4 * optim.numel, "loss": float(res[-1][1].item())}
+        del model, optim
         torch.cuda.empty_cache()
 
     # ---- CPU baseline beside it: rank 0, N=1 only, bounded sample, in its own process (all host threads)
@@ -460,20 +576,43 @@ def main():
             cpu = {"value": None, "unit": "ctx/s", "cores": None, "kind": "port", "sample": f"failed: {ex}"}
 
     if rank == 0:
+        cfg = bench_config(w, args)
         print(json.dumps({
             "metric": "path-contexts/sec", "value": value, "unit": "ctx/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "detail": w["desc"], "batch_per_gpu": B, "bag": L,
-                       "step": "Code2Vec.forward: encode + finalize + label logits + argmax",
-                       "algo": args.algo, "sharding": "methods sharded by rank, parameters replicated, no collective in forward",
-                       "l2": f"inputs larger than L2: {(w['T'] * w['Et'] + w['P'] * w['Ep']) * 4 / 1e6:.0f} MB of tables, "
-                             f"{nb} distinct batches ({nb * B * L * 24 / 1e6:.0f} MB of indices) cycled"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "train": train, "clocks": clocks,
-            "gpu_launches": int(lt.item()), "parity": parity,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "timing": {"passes": reps, "pass_ms_median": ms_max, "pass_ms_min": float(t.min().item()),
+                       "pass_ms_max": float(t.max().item()), "timed_region_s": timed_region_s, "algo": args.algo,
+                       "how": f"{reps} passes of exactly {args.steps} steps, each bracketed by barrier + synchronize and timed "
+                              "with CUDA events on the launch stream; max over ranks per pass, median over passes"},
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "e2e": e2e, "train": train,
+            "clocks": clocks, "gpu_launches": int(round(lt.item())), "parity": parity,
         }))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (GPUs 4-7 of an 8-GPU box sit on node 1): the host
+    loop of the e2e leg and its pinned staging buffers then live next to the GPU.  Returns what was done."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return f"gpu {bdf}: no NUMA affinity reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"gpu {bdf}: node {node} has no CPUs this process may use"
+        os.sched_setaffinity(0, cpus)
+        return f"gpu {bdf} -> NUMA node {node}, {len(cpus)} cpus"
+    except Exception as ex:
+        return f"not bound ({type(ex).__name__}: {ex})"
 
 
 if __name__ == "__main__":

@@ -17,6 +17,7 @@ bool pdl_enabled()
     return on == 1;
 }
 static thread_local char g_err[512] = "";
+thread_local bool g_pdl_this_call = true;
 
 void set_error(const char *fmt, ...)
 {
@@ -177,6 +178,7 @@ int c2v_encode_forward_stash(const c2v_dims *d, const c2v_params *p, const int64
         return C2V_EWORKSPACE;
     }
     const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;
+    g_pdl_this_call = (algo & C2V_FLAG_NO_PDL) == 0 && x_stash == nullptr;
     algo &= 0xff;
     bool use_tc;
     if (algo == C2V_ALGO_TCGEN05) {
@@ -300,6 +302,7 @@ int c2v_label_logits(const c2v_dims *d, const c2v_params *p, const float *code_v
     const int H = d->encode;
     const long long C = d->label_count;
     const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;
+    g_pdl_this_call = (algo & C2V_FLAG_NO_PDL) == 0;
     algo &= 0xff;
     if (algo == C2V_ALGO_TCGEN05 || (algo == C2V_ALGO_AUTO && label_tcgen05_shape_ok(d))) {
         return launch_label_tcgen05(d, code_vector, B, p->output_weight, p->output_bias, outputs, nullptr,
@@ -321,6 +324,7 @@ int c2v_label_logits_argmax(const c2v_dims *d, const c2v_params *p, const float 
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;
+    g_pdl_this_call = (algo & C2V_FLAG_NO_PDL) == 0;
     const int base_algo = algo & 0xff;
     if (base_algo == C2V_ALGO_TCGEN05 || (base_algo == C2V_ALGO_AUTO && label_tcgen05_shape_ok(d)))
         return launch_label_tcgen05(d, code_vector, B, p->output_weight, p->output_bias, outputs,

@@ -50,6 +50,9 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // stream is still draining; it must execute griddepcontrol.wait (pdl_wait()) before touching anything the previous
 // kernel wrote.  C2V_NO_PDL=1 falls back to a plain launch (A/B timing).
 bool pdl_enabled();
+// per-call switch (thread local, set by the extern "C" entry points): the calls that feed autograd -- the stashing training
+// forward, or any call with C2V_FLAG_NO_PDL -- use plain stream-ordered launches
+extern thread_local bool g_pdl_this_call;
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
 {
@@ -58,7 +61,7 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = (pdl_enabled() && g_pdl_this_call) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

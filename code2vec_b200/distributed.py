@@ -214,7 +214,7 @@ class ShardedFlatAdam:
         self.buckets[self.cur].zero_()
 
     # ---- the step -----------------------------------------------------------------------------------------------------
-    def _adam_slice(self, p_slice, g_slice):
+    def _adam_slice(self, p_slice, g_slice, zero_grad=False):
         """c2v_adam_step on the owned slice (the gloo CPU tests replace this method with a torch stand-in)"""
         import ctypes
         from . import _lib
@@ -223,8 +223,8 @@ class ShardedFlatAdam:
         dev = p_slice.device
         with torch.cuda.device(dev):
             rc = lib.c2v_adam_step(P(p_slice), P(g_slice), P(self.exp_avg), P(self.exp_avg_sq), p_slice.numel(), self.lr,
-                                   self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, 1.0 / self.world, 0,
-                                   ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                                   self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, 1.0 / self.world,
+                                   1 if zero_grad else 0, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc, "c2v_adam_step")
 
     def _reduce_scatter(self, out, full):
@@ -242,15 +242,16 @@ class ShardedFlatAdam:
         self.t += 1
         cur, nxt = self.cur, 1 - self.cur
         lo, hi = self.slice_begin, self.slice_begin + self.slice_n
-        if self.world == 1 or self.transport == "nccl":
-            if self.world > 1:
-                g_slice = torch.empty(self.slice_n, dtype=torch.float32, device=self.flat_param.device)
-                self._reduce_scatter(g_slice, self.buckets[cur])
-            else:
-                g_slice = self.buckets[cur][lo:hi]
+        if self.world == 1:                                      # one launch, gradient zeroed in the same pass, no swap
+            self._adam_slice(self.flat_param, self.buckets[cur], zero_grad=True)
+            for p in self.params:
+                torch.autograd.graph.increment_version(p)
+            return
+        if self.transport == "nccl":
+            g_slice = torch.empty(self.slice_n, dtype=torch.float32, device=self.flat_param.device)
+            self._reduce_scatter(g_slice, self.buckets[cur])
             self._adam_slice(self.flat_param[lo:hi], g_slice)
-            if self.world > 1:
-                dist.all_gather_into_tensor(self.flat_param, self.flat_param[lo:hi].clone(), group=self.group)
+            dist.all_gather_into_tensor(self.flat_param, self.flat_param[lo:hi].clone(), group=self.group)
             self.buckets[nxt].zero_()
         else:
             from . import _lib

@@ -68,6 +68,7 @@ def make_params(emb_t, emb_p, W, ln_g, ln_b, attn, w_out=None, b_out=None):
 
 
 REUSE_PREP = 0x100
+NO_PDL = 0x200
 
 
 class PrepCache:

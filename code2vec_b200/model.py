@@ -69,6 +69,8 @@ class _LabelFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cv, w_out, b_out, dims, algo, cache):
         params = CF.make_params(None, None, None, None, None, None, w_out, b_out)
+        if any(ctx.needs_input_grad[:3]):
+            algo = int(algo) | CF.NO_PDL            # the calls that feed autograd use plain stream-ordered launches
         out = CF.label_logits(dims, params, cv, algo, cache=cache, weight=w_out)
         ctx.save_for_backward(cv, w_out)
         ctx.dims = dims

@@ -61,6 +61,10 @@ enum {
  * hi-lo split copies of input_linear and output_linear kept in the workspace) are reused
  * instead of rebuilt.  The torch module sets it from the parameters' version counters. */
 #define C2V_FLAG_REUSE_PREP 0x100
+/* OR-ed into `algo`: launch this call's kernels as plain stream-ordered launches instead of programmatic dependent
+ * launches (the default overlaps each kernel's prologue with its predecessor's tail).  The training forward
+ * (c2v_encode_forward_stash with a stash) always does. */
+#define C2V_FLAG_NO_PDL 0x200
 
 /* Sizes read from the reference's Option (main.py:93-115) by Code2Vec.__init__
  * (model.py:18-42). */
