@@ -282,6 +282,26 @@ int64_t c2v_workspace_status(void *workspace, void *stream)
     return v;
 }
 
+int c2v_workspace_set_status_mirror(void *workspace, int64_t *pinned_host_word, void *stream)
+{
+    if (!workspace) { set_error("workspace is NULL"); return C2V_EINVAL; }
+    long long hdr[2] = {0, 0};
+    if (pinned_host_word) {
+        cudaPointerAttributes at;
+        C2V_CUDA_OK(cudaPointerGetAttributes(&at, pinned_host_word));
+        if (at.type != cudaMemoryTypeHost || !at.devicePointer) {
+            set_error("c2v_workspace_set_status_mirror: the mirror must be pinned (page-locked, device-mapped) host memory");
+            return C2V_EINVAL;
+        }
+        hdr[0] = (long long)reinterpret_cast<uintptr_t>(at.devicePointer);
+        hdr[1] = hdr[0] ^ C2V_MIRROR_MAGIC;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // pageable source: the copy is staged before the call returns, so the stack buffer may go away
+    C2V_CUDA_OK(cudaMemcpyAsync(static_cast<char *>(workspace) + 512, hdr, sizeof(hdr), cudaMemcpyHostToDevice, st));
+    return C2V_OK;
+}
+
 size_t c2v_label_workspace_bytes(const c2v_dims *d, int32_t B)
 {
     if (!dims_ok(d) || B < 1) return 0;
@@ -334,6 +354,58 @@ int c2v_label_logits_argmax(const c2v_dims *d, const c2v_params *p, const float 
     if (rc != C2V_OK || (!argmax && !maxval)) return rc;
     return launch_loss_argmax(outputs, nullptr, B, d->label_count, nullptr,
                               reinterpret_cast<long long *>(argmax), maxval, nullptr, st);
+}
+
+int c2v_label_loss_supported(const c2v_dims *d, int32_t B)
+{
+    if (!dims_ok(d) || B < 1) return 0;
+    return (label_tcgen05_shape_ok(d) && B <= 2048) ? 1 : 0;
+}
+
+int c2v_label_loss_argmax(const c2v_dims *d, const c2v_params *p, const float *code_vector, const int64_t *label,
+                          int32_t B, float *outputs, float *loss, float *lse, int64_t *argmax, float *maxval,
+                          void *workspace, size_t workspace_bytes, int32_t algo, void *stream)
+{
+    if (!dims_ok(d)) return C2V_EINVAL;
+    if (!p || !p->output_weight || !code_vector || !label || B < 1 || d->label_count < 1 || (!loss && !lse)) {
+        set_error("c2v_label_loss_argmax: bad argument");
+        return C2V_EINVAL;
+    }
+    if (!c2v_label_loss_supported(d, B)) {
+        set_error("c2v_label_loss_argmax: the fused loss needs encode_size %% 4 == 0, <= 256 and B <= 2048 (got %d, %d); use "
+                  "c2v_label_logits + c2v_loss_argmax", d->encode, B);
+        return C2V_EUNSUPPORTED;
+    }
+    const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;
+    g_pdl_this_call = (algo & C2V_FLAG_NO_PDL) == 0;
+    LabelLossArgs la;
+    memset(&la, 0, sizeof(la));
+    la.label = reinterpret_cast<const long long *>(label); la.loss = loss; la.lse_out = lse;
+    return launch_label_tcgen05_ex(d, code_vector, B, p->output_weight, p->output_bias, outputs,
+                                   reinterpret_cast<long long *>(argmax), maxval, workspace, workspace_bytes, reuse_prep,
+                                   static_cast<cudaStream_t>(stream), &la);
+}
+
+int c2v_label_dlogits(const c2v_dims *d, const c2v_params *p, const float *code_vector, const int64_t *label,
+                      const float *lse, int32_t B, float scale, const float *scale_device, float *d_outputs,
+                      void *workspace, size_t workspace_bytes, int32_t algo, void *stream)
+{
+    if (!dims_ok(d)) return C2V_EINVAL;
+    if (!p || !p->output_weight || !code_vector || !label || !lse || !d_outputs || B < 1 || d->label_count < 1) {
+        set_error("c2v_label_dlogits: bad argument");
+        return C2V_EINVAL;
+    }
+    if (!label_tcgen05_shape_ok(d)) {
+        set_error("c2v_label_dlogits: needs encode_size %% 4 == 0 and <= 256 (got %d)", d->encode);
+        return C2V_EUNSUPPORTED;
+    }
+    const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;
+    g_pdl_this_call = false;
+    LabelLossArgs la;
+    memset(&la, 0, sizeof(la));
+    la.label = reinterpret_cast<const long long *>(label); la.dlogits_lse = lse; la.dscale = scale; la.dscale_ptr = scale_device;
+    return launch_label_tcgen05_ex(d, code_vector, B, p->output_weight, p->output_bias, d_outputs, nullptr, nullptr,
+                                   workspace, workspace_bytes, reuse_prep, static_cast<cudaStream_t>(stream), &la);
 }
 
 int c2v_angular_logits(const c2v_dims *d, const c2v_params *p, const float *code_vector,

@@ -1,5 +1,5 @@
 // c2v_backward_dc_tc.cu -- K3c: dC = dX . W on the tensor cores + scatter into the embedding gradients
-// (terminal_embed = path_embed = encode = 128).
+// (terminal_embed = path_embed = E <= 128, encode = H <= 128, multiples of 4; zero-padded to 128 inside the panels).
 //
 // The gradient of the gathered context vectors (autograd of model.py:48-54 under loss.backward(), main.py:174):
 //   dC[r, d] = sum_h dX[r, h] * W[h, d],  then  dE_t[starts_r] += dC[r, 0:128], dE_p[paths_r] += dC[r, 128:256],
@@ -36,16 +36,16 @@ constexpr int IMG_BYTES = NB * B_SLOT;                // 192 KB
 
 // W [H=128][D=384] fp32 -> 6 tiles (sv * 2 + kb) of {hi, lo} [128 d x 64 h] fp16, K-major SWIZZLE_128B, scaled by the
 // power of two that lifts max |W| (bits in *absmax_bits, found by wt_absmax_kernel) just below 2^14.
-__global__ void wt_absmax_kernel(const float *__restrict__ W, unsigned *__restrict__ absmax_bits)
+__global__ void wt_absmax_kernel(const float *__restrict__ W, int n, unsigned *__restrict__ absmax_bits)
 {
     float m = 0.0f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dct::H * dct::D; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(W[i]));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(W[i]));
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0) atomicMax(absmax_bits, __float_as_uint(m));
 }
 __global__ void __launch_bounds__(256)
-split_wt_kernel(const float *__restrict__ W, const unsigned *__restrict__ absmax_bits, uint8_t *__restrict__ img,
-                float *__restrict__ hdr)
+split_wt_kernel(const float *__restrict__ W, int H, int E, const unsigned *__restrict__ absmax_bits,
+                uint8_t *__restrict__ img, float *__restrict__ hdr)
 {
     const float mx = __uint_as_float(*absmax_bits);
     float scale = 1.0f;
@@ -57,18 +57,20 @@ split_wt_kernel(const float *__restrict__ W, const unsigned *__restrict__ absmax
         scale = ldexpf(1.0f, k);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { hdr[0] = 1.0f / scale; hdr[1] = scale; }
-    // one thread = 4 consecutive d of one h (coalesced 16-B reads of W's rows)
+    // one thread = 4 consecutive d of one h of the PADDED [128 h][3 x 128 d] matrix (zeros beyond H / E); coalesced 16-B
+    // reads of W's rows ([H][3E] row-major)
     for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < dct::H * dct::D / 4; g += gridDim.x * blockDim.x) {
-        const int h = g / (dct::D / 4), d0 = (g % (dct::D / 4)) * 4;
-        const float4 w4 = *reinterpret_cast<const float4 *>(W + (size_t)h * dct::D + d0);
+        const int h = g / (dct::D / 4), dp = (g % (dct::D / 4)) * 4;
+        const int sv = dp / dct::E, dl = dp % dct::E, kb = h / 64, kk = h % 64;
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h < H && dl < E) w4 = *reinterpret_cast<const float4 *>(W + (size_t)h * (3 * E) + sv * E + dl);
         const float wv[4] = {w4.x * scale, w4.y * scale, w4.z * scale, w4.w * scale};
-        const int sv = d0 / dct::E, kb = h / 64, kk = h % 64;
         uint8_t *base = img + (size_t)(sv * 2 + kb) * dct::B_SLOT;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const __half hi = __float2half_rn(wv[q]);
             const __half lo = __float2half_rn(wv[q] - __half2float(hi));
-            const uint32_t off = sw128_offset(d0 % dct::E + q, kk);
+            const uint32_t off = sw128_offset(dl + q, kk);
             *reinterpret_cast<__half *>(base + off) = hi;
             *reinterpret_cast<__half *>(base + dct::PANEL + off) = lo;
         }
@@ -136,6 +138,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
             st_off[j] = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((q >> 1) ^ (r & 7)) & 7) << 4) + (q & 1) * 8);
         }
         const float4 *dx4 = reinterpret_cast<const float4 *>(dx);
+        const int H4 = a.H / 4;
         for (int tl = 0; tl < my_tiles; ++tl) {
             const long long row0 = ((long long)blockIdx.x + (long long)tl * gridDim.x) * dct::ROWS + pw * dct::ROWS_PER_PW;
             const int as = tl & 1;
@@ -145,7 +148,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const long long r = row0 + 2 * j + sub_row;
-                    float4 v = r < a.N ? ldg_nc_v4(dx4 + (size_t)r * (dct::H / 4) + p * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = (r < a.N && p * 16 + q < H4) ? ldg_nc_v4(dx4 + (size_t)r * H4 + p * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                     v.x *= dx_scale; v.y *= dx_scale; v.z *= dx_scale; v.w *= dx_scale;
                     buf[p][j] = v;
                 }
@@ -232,7 +235,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
             if (ie < 0 || ie >= a.T) ie = 0;
 #pragma unroll 1
             for (int sv = 0; sv < 3; ++sv) {
-                float *dst = sv == 1 ? g_emb_p + (size_t)ip * dct::E : g_emb_t + (size_t)(sv == 0 ? is : ie) * dct::E;
+                float *dst = sv == 1 ? g_emb_p + (size_t)ip * a.Et : g_emb_t + (size_t)(sv == 0 ? is : ie) * a.Et;
                 mbar_wait(bar_tfull + 8 * sv, (uint32_t)tl & 1u, status);
                 tc_fence_after();
 #pragma unroll 1
@@ -249,7 +252,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float v0 = v[j] * inv, v1 = v[j + 1] * inv, v2 = v[j + 2] * inv, v3 = v[j + 3] * inv;
-                            if (v0 != 0.0f || v1 != 0.0f || v2 != 0.0f || v3 != 0.0f)       // padded contexts: dx == 0
+                            if (c * 32 + j < a.Et && (v0 != 0.0f || v1 != 0.0f || v2 != 0.0f || v3 != 0.0f))   // padded contexts: dx == 0
                                 atomicAdd(reinterpret_cast<float4 *>(dst + c * 32 + j), make_float4(v0, v1, v2, v3));
                         }
                     }
@@ -265,7 +268,9 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
     }
 }
 
-bool backward_dc_tc_ok(const EncodeArgs &a) { return a.Et == dct::E && a.Ep == dct::E && a.H == dct::H; }
+bool backward_dc_tc_ok(const EncodeArgs &a) {
+    return a.Et == a.Ep && a.Et <= dct::E && a.H <= dct::H && (a.Et & 3) == 0 && (a.H & 3) == 0;
+}
 size_t backward_dc_tc_workspace_bytes() { return 1024 + dct::IMG_BYTES; }
 
 // ws: [0, 1024) header {1/scale, scale} | W^T image
@@ -278,9 +283,9 @@ int launch_backward_dc_tc(const EncodeArgs &a_in, const float *W, const float *d
     uint8_t *img = static_cast<uint8_t *>(ws) + 1024;
     unsigned *mxbits = reinterpret_cast<unsigned *>(static_cast<uint8_t *>(ws) + 512);
     C2V_CUDA_OK(cudaMemsetAsync(mxbits, 0, 4, st));
-    wt_absmax_kernel<<<48, 256, 0, st>>>(W, mxbits);
+    wt_absmax_kernel<<<48, 256, 0, st>>>(W, a.H * a.D, mxbits);
     C2V_LAUNCH_OK("wt_absmax_kernel");
-    split_wt_kernel<<<48, 256, 0, st>>>(W, mxbits, img, hdr);
+    split_wt_kernel<<<48, 256, 0, st>>>(W, a.H, a.Et, mxbits, img, hdr);
     C2V_LAUNCH_OK("split_wt_kernel");
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));

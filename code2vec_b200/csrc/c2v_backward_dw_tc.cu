@@ -1,4 +1,5 @@
-// c2v_backward_dw_tc.cu -- K3b: dW = dX^T . C on the tensor cores (terminal_embed = path_embed = encode = 128).
+// c2v_backward_dw_tc.cu -- K3b: dW = dX^T . C on the tensor cores (terminal_embed = path_embed = E <= 128, encode = H <= 128,
+// both multiples of 4: the reference's default 100/100/100 runs here with the panels zero-padded to 128).
 //
 // The weight gradient of input_linear (what autograd computes for model.py:54 under loss.backward(), main.py:174):
 //   dW[h, d] = sum over context rows r of dX[r, h] * C[r, d],   C[r] = [E_t[s_r]; E_p[p_r]; E_t[e_r]]
@@ -115,6 +116,7 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                 sts_v2(lo + st_off[j], pack_h2(l01), pack_h2(l23));
             }
         };
+        const int E4 = a.Et / 4, H4 = a.H / 4;        // row lengths in 16-byte pieces (columns beyond them are zero padding)
         const float4 *tab_t = reinterpret_cast<const float4 *>(a.emb_t);
         const float4 *tab_p = reinterpret_cast<const float4 *>(a.emb_p);
         const float4 *dx4 = reinterpret_cast<const float4 *>(dx);
@@ -128,7 +130,7 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
             if (is < 0 || is >= a.T) is = 0;
             if (ip < 0 || ip >= a.P) ip = 0;
             if (ie < 0 || ie >= a.T) ie = 0;
-            const uint32_t off_s = (uint32_t)(is * (dwt::E / 4)), off_p = (uint32_t)(ip * (dwt::E / 4)), off_e = (uint32_t)(ie * (dwt::E / 4));
+            const uint32_t off_s = (uint32_t)(is * E4), off_p = (uint32_t)(ip * E4), off_e = (uint32_t)(ie * E4);
             // ---- dX operand: two panels (h 0..63, 64..127) into tile-stage tl & 1
             const int as = tl & 1;
             mbar_wait(bar_aempty + 8 * as, (((uint32_t)(tl >> 1)) & 1u) ^ 1u, status);
@@ -138,7 +140,7 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const long long r = row0 + 2 * j + sub_row;
-                    buf[j] = r < a.N ? ldg_nc_v4(dx4 + (size_t)r * (dwt::H / 4) + p * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    buf[j] = (r < a.N && p * 16 + q < H4) ? ldg_nc_v4(dx4 + (size_t)r * H4 + p * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                     buf[j].x *= dx_scale; buf[j].y *= dx_scale; buf[j].z *= dx_scale; buf[j].w *= dx_scale;
                 }
                 const uint32_t hi = base + dwt::SMEM_A_OFF + as * dwt::A_STAGE + p * dwt::PANEL;
@@ -158,7 +160,7 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t o = __shfl_sync(0xffffffffu, off, 2 * j + sub_row);
                     const long long r = row0 + 2 * j + sub_row;
-                    buf[j] = r < a.N ? ldg_nc_v4(tab + (size_t)o + (kb & 1) * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    buf[j] = (r < a.N && (kb & 1) * 16 + q < E4) ? ldg_nc_v4(tab + (size_t)o + (kb & 1) * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 const int bs = itb & 1;
                 mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(itb >> 1)) & 1u) ^ 1u, status);
@@ -212,15 +214,20 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
         tc_fence_after();
         const int h = warp * 32 + lane;
         const float inv = 1.0f / dx_scale;
-        float *dst = dW + (size_t)h * dwt::D;
+        const int E = a.Et;
+        float *dst = dW + (size_t)h * (3 * E);                 // dW is [H][3E]; accumulator column sv * 128 + d
 #pragma unroll 1
         for (int c = 0; c < dwt::D / 32; ++c) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
             tmem_ld_wait();
+            const int sv = c >> 2, d0 = (c & 3) * 32;
+            if (h < a.H) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                atomicAdd(reinterpret_cast<float4 *>(dst + c * 32 + j), make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv));
+                for (int j = 0; j < 32; j += 4)
+                    if (d0 + j < E)
+                        atomicAdd(reinterpret_cast<float4 *>(dst + sv * E + d0 + j), make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv));
+            }
         }
         tc_fence_before();
     }
@@ -233,8 +240,8 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 }
 
 bool backward_dw_tc_ok(const EncodeArgs &a) {
-    return a.Et == dwt::E && a.Ep == dwt::E && a.H == dwt::H && (long long)a.T * dwt::E * 4 < (1ll << 32) &&
-           (long long)a.P * dwt::E * 4 < (1ll << 32);
+    return a.Et == a.Ep && a.Et <= dwt::E && a.H <= dwt::H && (a.Et & 3) == 0 && (a.H & 3) == 0 &&
+           (long long)a.T * a.Et * 4 < (1ll << 32) && (long long)a.P * a.Et * 4 < (1ll << 32);
 }
 
 int launch_backward_dw_tc(const EncodeArgs &a_in, const float *dx, const unsigned *dx_absmax, float *dW, cudaStream_t st)

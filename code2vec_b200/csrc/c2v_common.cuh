@@ -7,6 +7,7 @@
 
 #define C2V_NINF (-3.4e38f)   // model.py:12 (finite fp32, NOT -inf)
 #define C2V_LN_EPS 1e-5f       // nn.LayerNorm default, model.py:24
+#define C2V_MIRROR_MAGIC 0x0C2B200C0FFEE5A5LL   // guards the status-mirror pointer stored in the workspace header
 
 namespace c2v {
 
@@ -115,6 +116,18 @@ int launch_encode_finalize(const EncodeArgs &a, int B, float *code_vector, cudaS
 int launch_sgemm(int M, int N, int K, const float *A, long long a_sm, long long a_sk,
                  const float *B, long long b_sk, long long b_sn, const float *bias, float *C,
                  long long c_sm, bool accumulate, cudaStream_t st);
+// fused loss / dlogits modes of the label GEMM (c2v_label_tcgen05.cu)
+struct LabelLossArgs {
+    const long long *label;      // [B]
+    float *loss;                 // out: mean NLL (or NULL)
+    float *lse_out;              // out: [B] logsumexp of every row (or NULL)
+    const float *dlogits_lse;    // in: [B] -> `out` receives d loss / d logits instead of the logits (or NULL)
+    float dscale;                // dlogits scale: 1 / B (mean) ...
+    const float *dscale_ptr;     // ... times *dscale_ptr when not NULL (the upstream gradient of the scalar loss, on the device)
+};
+int launch_label_tcgen05_ex(const c2v_dims *d, const float *cv, int B, const float *Wout, const float *bias,
+                            float *out, long long *argmax, float *maxval, void *ws, size_t ws_bytes, bool reuse_prep,
+                            cudaStream_t st, const LabelLossArgs *la);
 int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float *Wout,
                          const float *bias, float *out, long long *argmax, float *maxval, void *ws,
                          size_t ws_bytes, bool reuse_prep, cudaStream_t st);

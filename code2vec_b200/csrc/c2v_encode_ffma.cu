@@ -167,8 +167,17 @@ encode_finalize_kernel(const EncodeArgs a, const int tile_rows, float *__restric
     pdl_wait();                                   // launched as a programmatic dependent of the encode kernel
     const long long bag = blockIdx.x;
     if (bag == 0 && threadIdx.x == 0) {           // publish + clear the out-of-range counter (c2v_api.cu)
-        a.ws.status[3] = a.ws.status[0];
+        const long long bad = a.ws.status[0];
+        a.ws.status[3] = bad;
         a.ws.status[0] = 0;
+        // host mirror (c2v_workspace_set_status_mirror): a pinned host word the caller polls at its next call, so that
+        // an out-of-range index raises IndexError without a synchronisation (the reference's CUDA device-assert is just
+        // as deferred).  Words 64 / 65 of the workspace: pointer and pointer ^ magic (never touched by the memsets).
+        long long *mirror = reinterpret_cast<long long *>(a.ws.status[64]);
+        if (bad != 0 && mirror != nullptr && a.ws.status[65] == (a.ws.status[64] ^ C2V_MIRROR_MAGIC)) {
+            atomicAdd_system(reinterpret_cast<unsigned long long *>(mirror), (unsigned long long)bad);
+            __threadfence_system();
+        }
     }
     const int L = a.L, H = a.H;
     const long long r0 = bag * L;

@@ -13,6 +13,8 @@
 
 #include <cstdlib>
 
+#include <cstring>
+
 #include "c2v_common.cuh"
 
 namespace c2v {
@@ -119,6 +121,22 @@ __device__ __forceinline__ LtTile lt_tile(long long t, int n_mt, long long n_nt,
     return r;
 }
 
+// Loss fusion (main.py:251-264): what the epilogue adds when the caller wants the mean NLL without
+// re-reading (or without ever writing) the [B, C] logits.
+//   part != NULL : per (row, n-tile, 32-column block) the block's (max, sum exp(v - max)) -> part[(nt * 4 + cq) * Mpad + row],
+//                  and the target logit v[row, label[row]] -> tgt[row]; merged by loss_partials_reduce / loss_finalize.
+//   lse  != NULL : dlogits mode (backward): the value stored is (exp(v - lse[row]) - [col == label[row]]) * dscale
+//                  instead of the logit (main.py:174 through log_softmax + NLLLoss, weights == 1).
+struct LtLoss {
+    float2 *part; float *tgt; const long long *label; const float *lse; const float *dscale_ptr; float dscale; int Mpad;
+};
+constexpr float LT_LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float lt_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 namespace lt2 {
 constexpr int NT_GROUP = 8;
 constexpr int N_EPI_WARPS = 16;                 // warp w: TMEM lane quarter w & 3, column quarter w >> 2 (32 columns)
@@ -149,7 +167,7 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
                      const float *__restrict__ bias, const float *__restrict__ hdr, float *__restrict__ out,
                      int M, long long N, int nkb, int n_mt, long long n_nt, long long n_tiles,
                      unsigned long long *__restrict__ keys, unsigned *__restrict__ ticket,
-                     long long *__restrict__ argmax, float *__restrict__ maxval, int dbg)
+                     long long *__restrict__ argmax, float *__restrict__ maxval, int dbg, const LtLoss ls)
 {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = lt_smem_u32(smem_raw);
@@ -289,6 +307,32 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
                 v[j] = fmaf(__uint_as_float(r[j]), inv_scale, b4.x); v[j + 1] = fmaf(__uint_as_float(r[j + 1]), inv_scale, b4.y);
                 v[j + 2] = fmaf(__uint_as_float(r[j + 2]), inv_scale, b4.z); v[j + 3] = fmaf(__uint_as_float(r[j + 3]), inv_scale, b4.w);
             }
+            if (ls.part || ls.lse) {
+                const long long grow = row0 + lane;                                     // this thread's output row
+                const long long lab = (grow < M && ls.label) ? ls.label[grow] : -1;
+                const long long tj = lab - col0;                                        // label's column inside this block
+                if (ls.part) {
+                    float m = -INFINITY, ssum = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m = fmaxf(m, j < n_cols ? v[j] : -INFINITY);
+                    const float mb = m * LT_LOG2E;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) ssum += j < n_cols ? lt_ex2(fmaf(v[j], LT_LOG2E, -mb)) : 0.0f;
+                    ls.part[(size_t)(nt * 4 + cq) * ls.Mpad + grow] = make_float2(m, n_cols > 0 ? ssum : 0.0f);
+                    if (__any_sync(0xffffffffu, tj >= 0 && tj < n_cols)) {
+                        float t = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) t = (j == (int)tj) ? v[j] : t;
+                        if (tj >= 0 && tj < n_cols) ls.tgt[grow] = t;
+                    }
+                }
+                if (ls.lse) {                                                           // dlogits (overwrites v)
+                    const float lb = (grow < M ? ls.lse[grow] : 0.0f) * LT_LOG2E;
+                    const float sc = ls.dscale_ptr ? ls.dscale * *ls.dscale_ptr : ls.dscale;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = (lt_ex2(fmaf(v[j], LT_LOG2E, -lb)) - ((j == (int)tj) ? 1.0f : 0.0f)) * sc;
+                }
+            }
             if (want_arg && lane < n_rows && n_cols > 0 && !C2V_EXPT(dbg, 2)) {
                 float m = -INFINITY;
                 if (n_cols == 32) {
@@ -307,6 +351,7 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
                     atomicMax(slot, ((unsigned long long)mk << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(col0 + jm)));
                 }
             }
+            if (out == nullptr) { __syncwarp(); continue; }   // loss-only mode: the logits are never written
             // registers -> padded smem tile (thread = row), then row-contiguous stores
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -369,6 +414,56 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
     }
 }
 
+// ---- merging the loss partials: (max, sum exp) pairs are merged online-softmax style ----------------------------------
+__device__ __forceinline__ void lt_merge(float &M, float &S, float m, float sv) {
+    if (m > M) { S = S * __expf(M - m) + sv; M = m; }          // (M = -inf, S = 0 start: exp(-inf) = 0)
+    else if (m > -INFINITY) S += sv * __expf(m - M);
+}
+constexpr int LT_PSPLIT = 16;
+// grid (Mpad / 32, LT_PSPLIT), 256 threads: lane = row, the 8 warps stride over this CTA's share of the partial index
+__global__ void __launch_bounds__(256)
+loss_partials_reduce_kernel(const float2 *__restrict__ part, int P, int Mpad, float2 *__restrict__ part2)
+{
+    __shared__ float2 sh[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = blockIdx.x * 32 + lane;
+    const int p0 = (int)((long long)P * blockIdx.y / gridDim.y), p1 = (int)((long long)P * (blockIdx.y + 1) / gridDim.y);
+    float M = -INFINITY, S = 0.0f;
+    for (int p = p0 + warp; p < p1; p += 8) {
+        const float2 v = part[(size_t)p * Mpad + row];
+        lt_merge(M, S, v.x, v.y);
+    }
+    sh[warp][lane] = make_float2(M, S);
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < 8; ++w) lt_merge(M, S, sh[w][lane].x, sh[w][lane].y);      // fixed order: deterministic
+        part2[(size_t)blockIdx.y * Mpad + row] = make_float2(M, S);
+    }
+}
+// one CTA: lse[b] = M + log S, loss = mean_b (lse[b] - target logit[b])   (main.py:251-264 with weights == 1)
+__global__ void __launch_bounds__(1024)
+loss_finalize_kernel(const float2 *__restrict__ part2, int nsplit, int Mpad, const float *__restrict__ tgt, int B,
+                     float *__restrict__ lse, float *__restrict__ loss)
+{
+    __shared__ float red[32];
+    float acc = 0.0f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float M = -INFINITY, S = 0.0f;
+        for (int k = 0; k < nsplit; ++k) { const float2 v = part2[(size_t)k * Mpad + b]; lt_merge(M, S, v.x, v.y); }
+        const float l = M + logf(S);
+        if (lse) lse[b] = l;
+        acc += l - tgt[b];
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0 && loss) *loss = v / (float)B;
+    }
+}
+
 // K (= encode_size) is zero-padded to a multiple of 64 inside the operand images
 bool label_tcgen05_shape_ok(const c2v_dims *d) { return d->encode >= 4 && d->encode <= 256 && (d->encode & 3) == 0; }
 
@@ -377,11 +472,17 @@ bool label_tcgen05_shape_ok(const c2v_dims *d) { return d->encode >= 4 && d->enc
 // batch of an evaluation pass has a different B).
 static size_t lt_keys_bytes(int B) { return (64 + (size_t)B * 8 + 1023) / 1024 * 1024; }
 
+// loss partials (behind the cv image): part [nt * 4][Mpad] float2 | part2 [LT_PSPLIT][Mpad] float2 | tgt [Mpad] float
+static size_t lt_loss_bytes(int B, long long C)
+{
+    const size_t Mpad = (size_t)(B + 127) / 128 * 128, nt = (size_t)((C + 127) / 128);
+    return (nt * 4 + LT_PSPLIT) * Mpad * sizeof(float2) + Mpad * sizeof(float) + 1024;
+}
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B)
 {
     const size_t nkb = (size_t)(d->encode + 63) / 64;
     const size_t mt = (size_t)(B + 127) / 128, nt = (size_t)(d->label_count + 127) / 128;
-    return 1024 + lt_keys_bytes(B) + (mt + nt) * nkb * 2 * lt::TILE_BYTES;
+    return 1024 + lt_keys_bytes(B) + (mt + nt) * nkb * 2 * lt::TILE_BYTES + lt_loss_bytes(B, d->label_count);
 }
 
 int launch_loss_argmax(const float *out, const long long *label, int B, long long C, float *loss,
@@ -389,9 +490,22 @@ int launch_loss_argmax(const float *out, const long long *label, int B, long lon
 
 // argmax / maxval (torch.max(dim=1), main.py:285) are folded into the GEMM epilogue (label_gemm_v2_kernel) for up to
 // 16 m-tiles (B <= 2048); beyond that they are a second pass over the logits.
+int launch_label_tcgen05_ex(const c2v_dims *d, const float *cv, int B, const float *Wout, const float *bias,
+                            float *out, long long *argmax, float *maxval, void *ws, size_t ws_bytes, bool reuse_prep,
+                            cudaStream_t st, const LabelLossArgs *la);
+
 int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float *Wout, const float *bias,
                          float *out, long long *argmax, float *maxval, void *ws, size_t ws_bytes, bool reuse_prep,
                          cudaStream_t st)
+{
+    return launch_label_tcgen05_ex(d, cv, B, Wout, bias, out, argmax, maxval, ws, ws_bytes, reuse_prep, st, nullptr);
+}
+
+// la != NULL: la->loss (mean NLL) / la->lse [B] are produced from the fused partials (out may then be NULL: the logits
+// are never written); la->dlogits_lse != NULL: `out` receives d(loss)/d(logits) instead of the logits.
+int launch_label_tcgen05_ex(const c2v_dims *d, const float *cv, int B, const float *Wout, const float *bias,
+                            float *out, long long *argmax, float *maxval, void *ws, size_t ws_bytes, bool reuse_prep,
+                            cudaStream_t st, const LabelLossArgs *la)
 {
     if (!label_tcgen05_shape_ok(d)) {
         set_error("tcgen05 label GEMM needs encode_size %% 4 == 0 and <= 256 (got %d)", d->encode);
@@ -414,6 +528,25 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
     unsigned *ticket = reinterpret_cast<unsigned *>(key_region);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(key_region + 64);
     uint8_t *imgA = key_region + lt_keys_bytes(B);
+    const int Mpad = (int)mt * 128;
+    float2 *part = reinterpret_cast<float2 *>(imgA + mt * nkb * 2 * lt::TILE_BYTES);
+    float2 *part2 = part + nt * 4 * (size_t)Mpad;
+    float *tgt = reinterpret_cast<float *>(part2 + (size_t)LT_PSPLIT * Mpad);
+    LtLoss ls;
+    memset(&ls, 0, sizeof(ls));
+    ls.Mpad = Mpad;
+    const bool want_loss = la && (la->loss || la->lse_out);
+    if (want_loss) {
+        if (!la->label) { set_error("label loss: label is NULL"); return C2V_EINVAL; }
+        ls.part = part; ls.tgt = tgt; ls.label = la->label;
+        // a label outside [0, C) leaves its target logit unwritten: NaN then makes the loss NaN (the reference's NLLLoss
+        // raises "Target out of bounds")
+        C2V_CUDA_OK(cudaMemsetAsync(tgt, 0xFF, (size_t)Mpad * sizeof(float), st));
+    }
+    if (la && la->dlogits_lse) {
+        if (!la->label || !out) { set_error("label dlogits: label / output is NULL"); return C2V_EINVAL; }
+        ls.lse = la->dlogits_lse; ls.label = la->label; ls.dscale = la->dscale; ls.dscale_ptr = la->dscale_ptr;
+    }
     const bool want_arg = argmax || maxval;
     const bool fused_arg = want_arg && mt <= (size_t)lt2::MAX_MT;
     int dev = 0, sms = 0;
@@ -440,9 +573,18 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
                            (const uint8_t *)imgA, (const uint8_t *)imgB, bias, (const float *)hdr, out, B, C, nkb, (int)mt,
                            (long long)nt, n_tiles, fused_arg ? keys : (unsigned long long *)nullptr, ticket,
                            fused_arg ? argmax : (long long *)nullptr, fused_arg ? maxval : (float *)nullptr,
-                           getenv("C2V_K2_FLAGS") ? atoi(getenv("C2V_K2_FLAGS")) : 0));
+                           getenv("C2V_K2_FLAGS") ? atoi(getenv("C2V_K2_FLAGS")) : 0, ls));
     C2V_LAUNCH_OK("label_gemm_v2_kernel");
-    if (want_arg && !fused_arg) return launch_loss_argmax(out, nullptr, B, C, nullptr, argmax, maxval, nullptr, st);
+    if (want_loss) {
+        loss_partials_reduce_kernel<<<dim3((unsigned)(Mpad / 32), LT_PSPLIT), 256, 0, st>>>(part, (int)(nt * 4), Mpad, part2);
+        C2V_LAUNCH_OK("loss_partials_reduce_kernel");
+        loss_finalize_kernel<<<1, 1024, 0, st>>>(part2, LT_PSPLIT, Mpad, tgt, B, la->lse_out, la->loss);
+        C2V_LAUNCH_OK("loss_finalize_kernel");
+    }
+    if (want_arg && !fused_arg) {
+        if (!out) { set_error("label loss without logits: arg-max needs B <= %d", lt2::MAX_MT * 128); return C2V_EUNSUPPORTED; }
+        return launch_loss_argmax(out, nullptr, B, C, nullptr, argmax, maxval, nullptr, st);
+    }
     return C2V_OK;
 }
 

@@ -280,8 +280,11 @@ class ShardedFlatAdam:
 def ddp_step(model, optimizer, bucket, starts, paths, ends, label, loss_fn):
     """One training step of main.py:171-175 on this rank's shard of the global batch."""
     if isinstance(optimizer, ShardedFlatAdam):               # reduction + optimizer + broadcast are one kernel per rank
-        outputs, code_vector, attention = model.forward(starts, paths, ends, label)
-        loss = loss_fn(outputs, label)
+        if loss_fn is None:                                  # fused loss: the [b, C] logits are never written
+            loss = model.forward_loss(starts, paths, ends, label)[0]
+        else:
+            outputs, code_vector, attention = model.forward(starts, paths, ends, label)
+            loss = loss_fn(outputs, label)
         loss.backward()
         optimizer.step()
         return loss

@@ -75,17 +75,40 @@ class PrepCache:
     """A persistent workspace whose derived weight images (split / transposed copies of a weight
     matrix) are rebuilt only when the weight changed: keyed on (data_ptr, _version, size)."""
 
-    def __init__(self):
+    def __init__(self, mirror_errors=False):
         self.buf, self.key = None, None
+        # encode workspaces: a pinned host word the finalize kernel adds its out-of-range index count to
+        # (c2v_workspace_set_status_mirror), polled by raise_deferred() at the next call on this cache
+        self.mirror_errors, self.err = mirror_errors, None       # (pinned memory needs the driver: allocated on first use)
 
     def get(self, nbytes, device, weight):
         key = (weight.data_ptr(), weight._version, str(device))
         fresh = self.buf is None or self.buf.numel() < nbytes or self.buf.device != device
         if fresh:
             self.buf = _empty((nbytes,), torch.uint8, device)
+            if self.mirror_errors:
+                if self.err is None:
+                    self.err = torch.zeros(1, dtype=torch.int64).pin_memory()
+                lib = _lib.load()
+                with torch.cuda.device(device):
+                    _lib.check(lib.c2v_workspace_set_status_mirror(_ptr(self.buf), ctypes.c_void_p(self.err.data_ptr()),
+                                                                   _stream(device)), "c2v_workspace_set_status_mirror")
         reuse = (not fresh) and key == self.key
         self.key = key
         return self.buf, reuse
+
+    def raise_deferred(self, synchronize=False):
+        """IndexError for out-of-range indices of an EARLIER forward on this cache (the kernels clamp them to row 0 and
+        count; the reference raises IndexError on CPU and device-asserts -- equally late -- on CUDA).  No sync unless asked."""
+        if self.err is None:
+            return
+        if synchronize and self.buf is not None:
+            torch.cuda.synchronize(self.buf.device)
+        n = int(self.err[0])
+        if n:
+            self.err[0] = 0
+            raise IndexError(f"index out of range in self ({n} start/path/end indices outside the embedding tables in an "
+                             "earlier forward of this module; they were read as row 0)")
 
 
 def encode_forward(dims, params, starts, paths, ends, drop_p=0.0, training=False, seed=0, algo=_lib.ALGO_AUTO,
@@ -169,6 +192,62 @@ def label_logits_argmax(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weigh
                                          _ptr(am), _ptr(mx), _ptr(ws), ws.numel(), int(algo), _stream(dev))
         _lib.check(rc, "c2v_label_logits_argmax")
     return out, am, mx
+
+
+def label_loss_supported(dims, B):
+    return bool(_lib.load().c2v_label_loss_supported(ctypes.byref(dims), int(B)))
+
+
+def label_loss(dims, params, cv, label, want_logits=False, algo=_lib.ALGO_AUTO, cache=None, weight=None):
+    """model.py:83 + main.py:251-264 + main.py:285 in one pass over the label GEMM's accumulators
+    -> (loss 0-d, lse [B], argmax int64 [B], maxval [B], outputs [B, C] or None).  With want_logits=False the [B, C]
+    logits are never written (nor re-read): the opt-in fast path of SURVEY.md 8f row 1."""
+    lib = _lib.load()
+    _need_cuda(cv, label)
+    B = cv.shape[0]
+    dev = cv.device
+    label = _idx(label, "label", (B,))
+    with torch.cuda.device(dev):
+        out = _empty((B, dims.label_count), torch.float32, dev) if want_logits else None
+        loss = _empty((), torch.float32, dev)
+        lse = _empty((B,), torch.float32, dev)
+        am = _empty((B,), torch.int64, dev)
+        mx = _empty((B,), torch.float32, dev)
+        nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
+        if cache is not None and weight is not None:
+            ws, reuse = cache.get(nbytes, dev, weight)
+            if reuse:
+                algo = int(algo) | REUSE_PREP
+        else:
+            ws = _empty((nbytes,), torch.uint8, dev)
+        cv = _f32c(cv, "code_vector")
+        rc = lib.c2v_label_loss_argmax(ctypes.byref(dims), ctypes.byref(params), _ptr(cv), _ptr(label), B, _ptr(out),
+                                       _ptr(loss), _ptr(lse), _ptr(am), _ptr(mx), _ptr(ws), ws.numel(), int(algo),
+                                       _stream(dev))
+        _lib.check(rc, "c2v_label_loss_argmax")
+    return loss, lse, am, mx, out
+
+
+def label_dlogits(dims, params, cv, label, lse, scale, scale_device=None, algo=_lib.ALGO_AUTO, cache=None, weight=None):
+    """d(mean NLL)/d(outputs) [B, C] = (softmax - onehot) * scale (* scale_device[0]), recomputed from cv and W_out"""
+    lib = _lib.load()
+    B = cv.shape[0]
+    dev = cv.device
+    with torch.cuda.device(dev):
+        dout = _empty((B, dims.label_count), torch.float32, dev)
+        nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
+        if cache is not None and weight is not None:
+            ws, reuse = cache.get(nbytes, dev, weight)
+            if reuse:
+                algo = int(algo) | REUSE_PREP
+        else:
+            ws = _empty((nbytes,), torch.uint8, dev)
+        cv = _f32c(cv, "code_vector"); lse = _f32c(lse, "lse")
+        sd = _f32c(scale_device, "scale_device") if scale_device is not None else None
+        rc = lib.c2v_label_dlogits(ctypes.byref(dims), ctypes.byref(params), _ptr(cv), _ptr(label), _ptr(lse), B,
+                                   float(scale), _ptr(sd), _ptr(dout), _ptr(ws), ws.numel(), int(algo), _stream(dev))
+        _lib.check(rc, "c2v_label_dlogits")
+    return dout
 
 
 def angular_logits(dims, params, cv, label, margin, inverse_temp):

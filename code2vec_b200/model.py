@@ -45,12 +45,15 @@ class _EncodeFn(torch.autograd.Function):
         ctx.x_stash = res[2] if stash else None
         ctx.save_for_backward(emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, cv, att)
         ctx.cfg = (dims, drop_p, training, seed)
+        ctx.cache = cache
         return cv, att
 
     @staticmethod
     def backward(ctx, d_cv, d_att):
         emb_t, emb_p, W, ln_g, ln_b, attn, starts, paths, ends, cv, att = ctx.saved_tensors
         dims, drop_p, training, seed = ctx.cfg
+        if ctx.cache is not None:
+            ctx.cache.raise_deferred()               # bad indices in the forward this backward belongs to
         params = CF.make_params(emb_t, emb_p, W, ln_g, ln_b, attn)
         shapes = {"terminal_embedding": emb_t.shape, "path_embedding": emb_p.shape, "input_linear": W.shape,
                   "ln_weight": ln_g.shape, "ln_bias": ln_b.shape, "attention": attn.shape}
@@ -83,6 +86,33 @@ class _LabelFn(torch.autograd.Function):
         d_cv, d_w, d_b = CF.label_backward(ctx.dims, params, cv, d_out, ctx.needs_input_grad[0],
                                            ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         return d_cv, d_w, d_b, None, None, None
+
+
+class _LabelLossFn(torch.autograd.Function):
+    """mean NLL of log_softmax(cv . W_out^T + b) (model.py:83 + main.py:251-264) without materialising the logits:
+    the label GEMM's epilogue produces loss / logsumexp / arg-max; the backward recomputes the tile-wise softmax."""
+
+    @staticmethod
+    def forward(ctx, cv, w_out, b_out, label, dims, algo, cache):
+        params = CF.make_params(None, None, None, None, None, None, w_out, b_out)
+        if any(ctx.needs_input_grad[:3]):
+            algo = int(algo) | CF.NO_PDL
+        loss, lse, am, mx, _ = CF.label_loss(dims, params, cv, label, want_logits=False, algo=algo, cache=cache, weight=w_out)
+        ctx.save_for_backward(cv, w_out, b_out, label, lse)
+        ctx.dims, ctx.cache, ctx.algo = dims, cache, algo
+        ctx.mark_non_differentiable(am, mx)
+        return loss, am, mx
+
+    @staticmethod
+    def backward(ctx, d_loss, _d_am, _d_mx):
+        cv, w_out, b_out, label, lse = ctx.saved_tensors
+        params = CF.make_params(None, None, None, None, None, None, w_out, b_out)
+        B = cv.shape[0]
+        d_out = CF.label_dlogits(ctx.dims, params, cv, label, lse, 1.0 / B, scale_device=d_loss.reshape(1),
+                                 algo=ctx.algo, cache=ctx.cache, weight=w_out)
+        d_cv, d_w, d_b = CF.label_backward(ctx.dims, params, cv, d_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                           ctx.needs_input_grad[2])
+        return d_cv, d_w, d_b, None, None, None, None
 
 
 class Code2Vec(nn.Module):
@@ -119,7 +149,7 @@ class Code2Vec(nn.Module):
         self._dropout_calls = 0
         # persistent workspaces: the hi/lo split images of input_linear / output_linear are rebuilt
         # only when the optimizer changed the weights (tracked by the tensors' version counters)
-        self._enc_cache = CF.PrepCache()
+        self._enc_cache = CF.PrepCache(mirror_errors=True)
         self._lab_cache = CF.PrepCache()
 
     # -- helpers ---------------------------------------------------------------------------
@@ -135,7 +165,13 @@ class Code2Vec(nn.Module):
         return int(torch.randint(0, 2 ** 62, (1,)).item())
 
     # -- the reference surface -------------------------------------------------------------
+    def check_indices(self):
+        """Synchronise and raise IndexError if any forward so far saw an index outside the embedding tables
+        (`forward` itself raises it one call late, without synchronising: see functional.PrepCache.raise_deferred)."""
+        self._enc_cache.raise_deferred(synchronize=True)
+
     def forward(self, starts, paths, ends, label):
+        self._enc_cache.raise_deferred()
         option = self.option
         dims = self._dims()
         training = self.training and self.input_dropout is not None
@@ -168,12 +204,40 @@ class Code2Vec(nn.Module):
 
         return outputs, code_vector, attention
 
+    # -- additive fast path: forward + calculate_loss (main.py:251-264) + torch.max (main.py:285) -----
+    def forward_loss(self, starts, paths, ends, label):
+        """-> (loss, pred_label [b], pred_score [b], code_vector [b,H], attention [b,L]); loss is the mean NLL the
+        reference's `calculate_loss(preds, label, criterion, option)` returns (criterion weights are all 1, SURVEY 8a
+        row 16) and is autograd-connected; the [b, C] logits are never written.  Plain label head only; shapes the fused
+        kernel does not take fall back to forward() + c2v_loss_argmax."""
+        if self.option.angular_margin_loss:
+            raise NotImplementedError("forward_loss() needs the plain label head")
+        self._enc_cache.raise_deferred()
+        dims = self._dims()
+        training = self.training and self.input_dropout is not None
+        drop_p = float(self.option.dropout_prob) if training else 0.0
+        seed = self._next_seed() if training else 0
+        code_vector, attention = _EncodeFn.apply(
+            self.terminal_embedding.weight, self.path_embedding.weight, self.input_linear.weight,
+            self.input_layer_norm.weight, self.input_layer_norm.bias, self.attention_parameter,
+            starts, paths, ends, dims, drop_p, training, seed, self.algo, self._enc_cache)
+        if self.algo != _lib.ALGO_FFMA and CF.label_loss_supported(dims, starts.shape[0]):
+            loss, am, mx = _LabelLossFn.apply(code_vector, self.output_linear.weight, self.output_linear.bias, label, dims,
+                                              _lib.ALGO_AUTO, self._lab_cache)
+        else:
+            outputs = _LabelFn.apply(code_vector, self.output_linear.weight, self.output_linear.bias, dims,
+                                     _lib.ALGO_FFMA if self.algo == _lib.ALGO_FFMA else _lib.ALGO_AUTO, self._lab_cache)
+            loss = F.nll_loss(F.log_softmax(outputs, dim=1), label)
+            mx, am = torch.max(outputs.detach(), dim=1)
+        return loss, am, mx, code_vector, attention
+
     # -- additive convenience (the reference does torch.max(preds, dim=1) at main.py:285) ----
     @torch.no_grad()
     def predict(self, starts, paths, ends):
         """-> (pred_label [b], pred_score [b], code_vector [b,H], attention [b,L])"""
         if self.option.angular_margin_loss:
             raise NotImplementedError("predict() needs the plain label head (the angular head needs labels)")
+        self._enc_cache.raise_deferred()
         dims = self._dims()
         params = CF.make_params(self.terminal_embedding.weight, self.path_embedding.weight, self.input_linear.weight,
                                 self.input_layer_norm.weight, self.input_layer_norm.bias, self.attention_parameter,

@@ -149,6 +149,11 @@ int c2v_encode_forward_stash(const c2v_dims *d, const c2v_params *p, const int64
 /* Reads the status word of the last encode on this workspace (synchronises the
  * stream): returns the number of out-of-range indices seen, or a negative code. */
 int64_t c2v_workspace_status(void *workspace, void *stream);
+/* Deferred error surface for device callers: registers a pinned (page-locked) host int64 with an encode workspace; every
+ * later c2v_encode_forward* on that workspace ADDS its count of out-of-range indices to the host word (nothing is written
+ * when the count is 0), so the caller can poll the word at its next call -- no synchronisation -- and raise IndexError, as
+ * late as the reference's own CUDA device assert would (SURVEY.md 8b "Call").  NULL unregisters. */
+int c2v_workspace_set_status_mirror(void *workspace, int64_t *pinned_host_word, void *stream);
 
 /* ---- label head --------------------------------------------------------------------
  * plain:   outputs = cv . W_out^T + b                                   model.py:83
@@ -159,6 +164,22 @@ size_t c2v_label_workspace_bytes(const c2v_dims *d, int32_t B);
 int c2v_label_logits(const c2v_dims *d, const c2v_params *p, const float *code_vector, int32_t B,
                      float *outputs, void *workspace, size_t workspace_bytes, int32_t algo,
                      void *stream);
+/* Loss fused into the label GEMM: model.py:83 + calculate_loss (main.py:251-264: log_softmax +
+ * NLLLoss with weights == 1, mean over the batch) + torch.max(dim=1) (main.py:285) in one pass.  The epilogue of the
+ * label kernel keeps, per row, (max, sum exp) partials, the target logit and the running arg-max, so the [B, C] logits
+ * are never re-read -- and with outputs == NULL never written (800 MB per batch at the top11 label count).
+ * loss: mean NLL (device scalar), lse: [B] logsumexp per row (what the backward needs), either may be NULL (not both).
+ * Same workspace as c2v_label_logits.  c2v_label_loss_supported: encode_size % 4 == 0, <= 256, B <= 2048. */
+int c2v_label_loss_supported(const c2v_dims *d, int32_t B);
+int c2v_label_loss_argmax(const c2v_dims *d, const c2v_params *p, const float *code_vector, const int64_t *label,
+                          int32_t B, float *outputs, float *loss, float *lse, int64_t *argmax, float *maxval,
+                          void *workspace, size_t workspace_bytes, int32_t algo, void *stream);
+/* Backward companion: recomputes the logits tile by tile and writes d loss / d outputs [B, C] =
+ * (softmax(outputs) - onehot(label)) * scale (* *scale_device when not NULL: the upstream gradient of the scalar loss;
+ * scale = 1 / B for the mean) straight from the accumulators; feed it to c2v_label_backward. */
+int c2v_label_dlogits(const c2v_dims *d, const c2v_params *p, const float *code_vector, const int64_t *label,
+                      const float *lse, int32_t B, float scale, const float *scale_device, float *d_outputs,
+                      void *workspace, size_t workspace_bytes, int32_t algo, void *stream);
 /* Label logits + the prediction the reference takes from them (`torch.max(preds, dim=1)`,
  * main.py:285; first maximum wins) in one call: the argmax pass runs right behind the GEMM while the
  * [B,C] logits are still in L2.  argmax int64 [B], maxval fp32 [B] (either may be NULL). */
