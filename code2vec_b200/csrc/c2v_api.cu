@@ -31,7 +31,10 @@ int launch_transpose_w(const float *W, float *Wt, int H, int D, int Hs, cudaStre
 int launch_split_w_tcgen05(const c2v_dims *d, const float *W, EncodeWorkspace &ws, cudaStream_t st);
 int launch_angular(const c2v_dims *d, const c2v_params *p, const float *cv, const long long *label,
                    int B, float margin, float inverse_temp, float *out, float *scratch,
-                   cudaStream_t st);
+                   cudaStream_t st, float *cos_out);
+int launch_angular_backward(const c2v_dims *d, const c2v_params *p, const float *cv, const long long *label, int B,
+                            float margin, float inverse_temp, const float *cosine, const float *inv_cv, const float *inv_w,
+                            float *d_out_inplace, float *d_cv, float *d_w, float *sums, cudaStream_t st);
 int launch_loss_argmax(const float *out, const long long *label, int B, long long C, float *loss,
                        long long *argmax, float *maxval, float *d_out, cudaStream_t st);
 int launch_colsum(const float *X, int B, long long C, float *out, cudaStream_t st);
@@ -421,9 +424,36 @@ int c2v_angular_logits(const c2v_dims *d, const c2v_params *p, const float *code
     float *scratch = nullptr;
     C2V_CUDA_OK(cudaMallocAsync(&scratch, (size_t)(B + d->label_count) * sizeof(float), st));
     int rc = launch_angular(d, p, code_vector, reinterpret_cast<const long long *>(label), B, margin,
-                            inverse_temp, outputs, scratch, st);
+                            inverse_temp, outputs, scratch, st, nullptr);
     cudaFreeAsync(scratch, st);
     return rc;
+}
+
+int c2v_angular_forward_train(const c2v_dims *d, const c2v_params *p, const float *code_vector, const int64_t *label,
+                              int32_t B, float margin, float inverse_temp, float *outputs, float *cosine,
+                              float *inv_norms, void *stream)
+{
+    if (!dims_ok(d)) return C2V_EINVAL;
+    if (!p || !p->output_weight || !code_vector || !outputs || !label || !cosine || !inv_norms || B < 1) {
+        set_error("c2v_angular_forward_train: bad argument");
+        return C2V_EINVAL;
+    }
+    return launch_angular(d, p, code_vector, reinterpret_cast<const long long *>(label), B, margin, inverse_temp, outputs,
+                          inv_norms, static_cast<cudaStream_t>(stream), cosine);
+}
+
+int c2v_angular_backward(const c2v_dims *d, const c2v_params *p, const float *code_vector, const int64_t *label,
+                         int32_t B, float margin, float inverse_temp, const float *cosine, const float *inv_norms,
+                         float *d_outputs, float *d_code_vector, float *d_output_weight, float *scratch, void *stream)
+{
+    if (!dims_ok(d)) return C2V_EINVAL;
+    if (!p || !p->output_weight || !code_vector || !label || !cosine || !inv_norms || !d_outputs || !scratch || B < 1) {
+        set_error("c2v_angular_backward: bad argument");
+        return C2V_EINVAL;
+    }
+    return launch_angular_backward(d, p, code_vector, reinterpret_cast<const long long *>(label), B, margin, inverse_temp,
+                                   cosine, inv_norms, inv_norms + B, d_outputs, d_code_vector, d_output_weight, scratch,
+                                   static_cast<cudaStream_t>(stream));
 }
 
 int c2v_loss_argmax(const float *outputs, const int64_t *label, int32_t B, int64_t C, float *loss,

@@ -115,13 +115,14 @@ __global__ void row_inv_norm_kernel(const float *__restrict__ X, long long rows,
 __global__ void angular_epilogue_kernel(float *__restrict__ out, const float *__restrict__ inv_cv,
                                         const float *__restrict__ inv_w,
                                         const long long *__restrict__ label, int B, long long C,
-                                        float cos_m, float sin_m, float inv_temp)
+                                        float cos_m, float sin_m, float inv_temp, float *__restrict__ cos_out)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * C) return;
     const int b = (int)(i / C);
     const long long c = i % C;
     const float cosv = out[i] * inv_cv[b] * inv_w[c];
+    if (cos_out) cos_out[i] = cosv;                        // kept for the backward (training)
     const float sinv = sqrtf(1.0f - cosv * cosv);
     float phi = cosv * cos_m - sinv * sin_m;
     if (!(cosv > 0.0f)) phi = cosv;
@@ -130,7 +131,7 @@ __global__ void angular_epilogue_kernel(float *__restrict__ out, const float *__
 
 int launch_angular(const c2v_dims *d, const c2v_params *p, const float *cv, const long long *label,
                    int B, float margin, float inverse_temp, float *out, float *scratch,
-                   cudaStream_t st)
+                   cudaStream_t st, float *cos_out)
 {
     const int H = d->encode;
     const long long C = d->label_count;
@@ -143,9 +144,75 @@ int launch_angular(const c2v_dims *d, const c2v_params *p, const float *cv, cons
     if (rc != C2V_OK) return rc;
     const long long n = (long long)B * C;
     angular_epilogue_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-        out, inv_cv, inv_w, label, B, C, cosf(margin), sinf(margin), inverse_temp);
+        out, inv_cv, inv_w, label, B, C, cosf(margin), sinf(margin), inverse_temp, cos_out);
     C2V_LAUNCH_OK("angular_epilogue_kernel");
     return C2V_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// backward of the angular-margin head (autograd of model.py:71-80):
+//   out = s (onehot phi + (1 - onehot) cos),  phi = cos > 0 ? cos cos_m - sin sin_m : cos,  sin = sqrt(1 - cos^2),
+//   cos[b,c] = dot[b,c] icv[b] iw[c],  dot = cv . W^T,  icv = 1 / max(|cv_b|, 1e-12),  iw likewise (F.normalize)
+//   dcos = s d_out (target column with cos > 0: x (cos_m + sin_m cos / sin));   G = dcos icv iw  (= d loss / d dot)
+//   d_cv = G . W   - icv_b^2 (sum_c dcos cos) cv_b ;   d_W = G^T . cv - iw_c^2 (sum_b dcos cos) W_c
+// angular_dcos_kernel overwrites d_out with G and accumulates the two correction sums; the GEMMs are launch_sgemm.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+angular_dcos_kernel(float *__restrict__ g, const float *__restrict__ cosv, const float *__restrict__ inv_cv,
+                    const float *__restrict__ inv_w, const long long *__restrict__ label, int B, long long C,
+                    float cos_m, float sin_m, float inv_temp, float *__restrict__ rowsum, float *__restrict__ colsum)
+{
+    const int b = blockIdx.y;
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float pc = 0.0f;
+    if (c < C) {
+        const size_t i = (size_t)b * C + c;
+        const float co = cosv[i];
+        float dcos = g[i] * inv_temp;
+        if (label[b] == c && co > 0.0f) dcos *= cos_m + sin_m * co / sqrtf(1.0f - co * co);
+        g[i] = dcos * inv_cv[b] * inv_w[c];
+        pc = dcos * co;
+        if (pc != 0.0f) atomicAdd(colsum + c, pc);
+    }
+    pc = warp_sum(pc);
+    if ((threadIdx.x & 31) == 0 && pc != 0.0f) atomicAdd(rowsum + b, pc);
+}
+__global__ void angular_fix_rows_kernel(float *__restrict__ d, const float *__restrict__ x, const float *__restrict__ inv,
+                                        const float *__restrict__ sums, long long rows, int H)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * H) return;
+    const long long r = i / H;
+    d[i] = fmaf(-inv[r] * inv[r] * sums[r], x[i], d[i]);
+}
+
+int launch_angular_backward(const c2v_dims *d, const c2v_params *p, const float *cv, const long long *label, int B,
+                            float margin, float inverse_temp, const float *cosine, const float *inv_cv, const float *inv_w,
+                            float *d_out_inplace, float *d_cv, float *d_w, float *sums, cudaStream_t st)
+{
+    const int H = d->encode;
+    const long long C = d->label_count;
+    float *rowsum = sums, *colsum = sums + B;
+    C2V_CUDA_OK(cudaMemsetAsync(sums, 0, (size_t)(B + C) * sizeof(float), st));
+    angular_dcos_kernel<<<dim3((unsigned)((C + 255) / 256), (unsigned)B), 256, 0, st>>>(
+        d_out_inplace, cosine, inv_cv, inv_w, label, B, C, cosf(margin), sinf(margin), inverse_temp, rowsum, colsum);
+    C2V_LAUNCH_OK("angular_dcos_kernel");
+    int rc = C2V_OK;
+    if (d_cv) {
+        rc = launch_sgemm(B, H, (int)C, d_out_inplace, C, 1, p->output_weight, H, 1, nullptr, d_cv, H, false, st);
+        if (rc != C2V_OK) return rc;
+        const long long n = (long long)B * H;
+        angular_fix_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_cv, cv, inv_cv, rowsum, B, H);
+        C2V_LAUNCH_OK("angular_fix_rows_kernel");
+    }
+    if (d_w) {
+        rc = launch_sgemm((int)C, H, B, d_out_inplace, 1, C, cv, H, 1, nullptr, d_w, H, false, st);
+        if (rc != C2V_OK) return rc;
+        const long long n = C * H;
+        angular_fix_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_w, p->output_weight, inv_w, colsum, C, H);
+        C2V_LAUNCH_OK("angular_fix_rows_kernel");
+    }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------

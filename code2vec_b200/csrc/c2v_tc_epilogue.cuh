@@ -51,6 +51,24 @@ __device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *
         for (int s = 0; s < NS; ++s) t += qx[(s * 3 + slot) * 32];
         return t;
     };
+#ifdef TCE_ONEPASS_LN
+    // LayerNorm (model.py:55-56), one pass: sum and sum of squares together (one exchange between the slices instead of
+    // two); padding columns are exactly 0 and drop out of both.  var = E[x^2] - mean^2 in fp32: relative error
+    // ~2^-24 (1 + mean^2 / var), far inside the 1e-4 budget for the row statistics of c . W^T.
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int c = 0; c < HC; c += 4) {
+        s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3];
+        q0 = fmaf(x[c], x[c], q0); q1 = fmaf(x[c + 1], x[c + 1], q1); q2 = fmaf(x[c + 2], x[c + 2], q2); q3 = fmaf(x[c + 3], x[c + 3], q3);
+    }
+    float part = (s0 + s1) + (s2 + s3);
+    my_x[0] = part;
+    my_x[32] = (q0 + q1) + (q2 + q3);
+    named_bar_sync(1 + q, 32 * NS);
+    const float mean = xsum(0) * inv_h;
+    const float var = fmaxf(fmaf(-mean, mean, xsum(1) * inv_h), 0.0f) * inv_scale * inv_scale;
+    (void)vlast;
+#else
     // LayerNorm (model.py:55-56), two-pass; x is scale * (c . W^T); slices exchanged via smem
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
@@ -73,6 +91,7 @@ __device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *
     my_x[32] = part;
     named_bar_sync(1 + q, 32 * NS);
     const float var = xsum(1) * inv_h * inv_scale * inv_scale;
+#endif
     const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
     const float shift = -mean * nrm;
     // tanh (model.py:57), dropout (model.py:60-61), score h.a (model.py:92-93)

@@ -266,6 +266,42 @@ def angular_logits(dims, params, cv, label, margin, inverse_temp):
     return out
 
 
+def angular_forward_train(dims, params, cv, label, margin, inverse_temp):
+    """model.py:71-80 for a forward that will be differentiated -> (outputs, cosine [B, C], inv_norms [B + C])"""
+    lib = _lib.load()
+    _need_cuda(cv, label)
+    B = cv.shape[0]
+    dev = cv.device
+    label = _idx(label, "label", (B,))
+    with torch.cuda.device(dev):
+        out = _empty((B, dims.label_count), torch.float32, dev)
+        cos = _empty((B, dims.label_count), torch.float32, dev)
+        inv = _empty((B + dims.label_count,), torch.float32, dev)
+        cv = _f32c(cv, "code_vector")
+        rc = lib.c2v_angular_forward_train(ctypes.byref(dims), ctypes.byref(params), _ptr(cv), _ptr(label), B, float(margin),
+                                           float(inverse_temp), _ptr(out), _ptr(cos), _ptr(inv), _stream(dev))
+        _lib.check(rc, "c2v_angular_forward_train")
+    return out, cos, inv
+
+
+def angular_backward(dims, params, cv, label, margin, inverse_temp, cos, inv, d_out, need_cv=True, need_w=True):
+    """-> (d_code_vector, d_output_weight); d_out is consumed (overwritten)"""
+    lib = _lib.load()
+    B = cv.shape[0]
+    dev = cv.device
+    with torch.cuda.device(dev):
+        d_out = _f32c(d_out, "d_outputs").clone()            # the kernel overwrites it; autograd's grad tensor is not ours
+        d_cv = torch.empty_like(cv) if need_cv else None
+        d_w = _empty((dims.label_count, dims.encode), torch.float32, dev) if need_w else None
+        scratch = _empty((B + dims.label_count,), torch.float32, dev)
+        cv = _f32c(cv, "code_vector")
+        rc = lib.c2v_angular_backward(ctypes.byref(dims), ctypes.byref(params), _ptr(cv), _ptr(label), B, float(margin),
+                                      float(inverse_temp), _ptr(cos), _ptr(inv), _ptr(d_out), _ptr(d_cv), _ptr(d_w),
+                                      _ptr(scratch), _stream(dev))
+        _lib.check(rc, "c2v_angular_backward")
+    return d_cv, d_w
+
+
 def loss_argmax(outputs, label=None, want_grad=False):
     """main.py:251-264 + main.py:285 -> (loss 0-d or None, argmax [B], maxval [B], d_outputs or None)"""
     lib = _lib.load()

@@ -88,6 +88,27 @@ class _LabelFn(torch.autograd.Function):
         return d_cv, d_w, d_b, None, None, None
 
 
+class _AngularFn(torch.autograd.Function):
+    """angular-margin head (model.py:71-80) with its hand-written backward (c2v_angular_backward)"""
+
+    @staticmethod
+    def forward(ctx, cv, w_out, label, dims, margin, inverse_temp):
+        params = CF.make_params(None, None, None, None, None, None, w_out, None)
+        out, cos, inv = CF.angular_forward_train(dims, params, cv, label, margin, inverse_temp)
+        ctx.save_for_backward(cv, w_out, label, cos, inv)
+        ctx.cfg = (dims, margin, inverse_temp)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        cv, w_out, label, cos, inv = ctx.saved_tensors
+        dims, margin, inverse_temp = ctx.cfg
+        params = CF.make_params(None, None, None, None, None, None, w_out, None)
+        d_cv, d_w = CF.angular_backward(dims, params, cv, label, margin, inverse_temp, cos, inv, d_out,
+                                        ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return d_cv, d_w, None, None, None, None
+
+
 class _LabelLossFn(torch.autograd.Function):
     """mean NLL of log_softmax(cv . W_out^T + b) (model.py:83 + main.py:251-264) without materialising the logits:
     the label GEMM's epilogue produces loss / logsumexp / arg-max; the backward recomputes the tile-wise softmax."""
@@ -185,15 +206,8 @@ class Code2Vec(nn.Module):
 
         if option.angular_margin_loss:
             if torch.is_grad_enabled() and (code_vector.requires_grad or self.output_linear.requires_grad):
-                # training through the optional angular head: autograd over torch ops
-                # (SURVEY.md 8a row 14 allows a PyTorch epilogue for this mode)
-                cosine = F.linear(F.normalize(code_vector), F.normalize(self.output_linear))
-                sine = torch.sqrt(1.0 - torch.pow(cosine, 2))
-                phi = cosine * self.cos_m - sine * self.sin_m
-                phi = torch.where(cosine > 0, phi, cosine)
-                one_hot = torch.zeros(cosine.size(), device=cosine.device)
-                one_hot.scatter_(1, label.view(-1, 1).long(), 1)
-                outputs = ((one_hot * phi) + ((1.0 - one_hot) * cosine)) * option.inverse_temp
+                outputs = _AngularFn.apply(code_vector, self.output_linear, label, dims, option.angular_margin,
+                                           option.inverse_temp)
             else:
                 params = CF.make_params(None, None, None, None, None, None, self.output_linear, None)
                 outputs = CF.angular_logits(dims, params, code_vector, label, option.angular_margin, option.inverse_temp)

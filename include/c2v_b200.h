@@ -164,6 +164,18 @@ size_t c2v_label_workspace_bytes(const c2v_dims *d, int32_t B);
 int c2v_label_logits(const c2v_dims *d, const c2v_params *p, const float *code_vector, int32_t B,
                      float *outputs, void *workspace, size_t workspace_bytes, int32_t algo,
                      void *stream);
+/* Training through the angular-margin head (model.py:71-80 under loss.backward(), main.py:174).
+ * c2v_angular_forward_train = c2v_angular_logits that also keeps cosine [B, C] and inv_norms [B + C]
+ * (1 / max(|cv_b|, 1e-12) then 1 / max(|W_c|, 1e-12), F.normalize's clamp) for the backward.
+ * c2v_angular_backward: d_outputs [B, C] is OVERWRITTEN (it becomes d loss / d (cv . W^T)); d_code_vector [B, H] and
+ * d_output_weight [C, H] are written (either may be NULL); scratch: B + C floats. */
+int c2v_angular_forward_train(const c2v_dims *d, const c2v_params *p, const float *code_vector, const int64_t *label,
+                              int32_t B, float margin, float inverse_temp, float *outputs, float *cosine,
+                              float *inv_norms, void *stream);
+int c2v_angular_backward(const c2v_dims *d, const c2v_params *p, const float *code_vector, const int64_t *label,
+                         int32_t B, float margin, float inverse_temp, const float *cosine, const float *inv_norms,
+                         float *d_outputs, float *d_code_vector, float *d_output_weight, float *scratch, void *stream);
+
 /* Loss fused into the label GEMM: model.py:83 + calculate_loss (main.py:251-264: log_softmax +
  * NLLLoss with weights == 1, mean over the batch) + torch.max(dim=1) (main.py:285) in one pass.  The epilogue of the
  * label kernel keeps, per row, (max, sum exp) partials, the target logit and the running arg-max, so the [B, C] logits

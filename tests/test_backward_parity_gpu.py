@@ -217,3 +217,19 @@ def test_flat_adam_matches_torch_adam_over_several_steps(wd):
             assert n1 == n2
             assert (p1 - p2).abs().max().item() <= 3e-6 * max(1.0, p2.abs().max().item()), (step, n1)
     assert l1.item() < float(rec["loss"])            # it does learn
+
+
+@pytest.mark.parametrize("name", ["angular_grad", "angular_grad128"])
+def test_angular_head_gradients_match_reference_autograd(name):
+    """training through the angular-margin head (model.py:71-80): c2v_angular_forward_train / c2v_angular_backward
+    against the gradients the unmodified reference's autograd produced (oracle/gen_golden.py)"""
+    rec = load_golden(name)
+    m = model_from_golden(rec).train()
+    out, cv, att = m.forward(cuda(rec["starts"]), cuda(rec["paths"]), cuda(rec["ends"]), cuda(rec["label"]))
+    assert np.abs(out.detach().cpu().numpy() - rec["outputs"]).max() <= 1e-4
+    loss = F.nll_loss(F.log_softmax(out, dim=1), cuda(rec["label"]))
+    assert abs(loss.item() - float(rec["loss"])) <= 1e-5 * max(1.0, abs(float(rec["loss"])))
+    loss.backward()
+    for k, p in m.named_parameters():
+        ref = rec["grads"][k]
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= _tol(ref), k
