@@ -252,6 +252,30 @@ __device__ __forceinline__ void tce_epilogue_loop_wide(const EncodeArgs &a, floa
         mbar_wait(bar_tfull, (uint32_t)tl & 1u, status);
         tc_fence_after();
         float x[CH];
+#ifdef TCE_ONEPASS_LN
+        // pass 1: sum and sum of squares together (model.py:55-56; see tce_tile_body): one walk over the accumulator less
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            load_chunk(ch, x);
+            if (a.stash_x && in_range) {
+                float4 *dst = reinterpret_cast<float4 *>(a.stash_x + (size_t)row * a.H + hf * HS + ch * CH);
+#pragma unroll
+                for (int c = 0; c < CH; c += 4)
+                    dst[c / 4] = make_float4(x[c] * inv_scale, x[c + 1] * inv_scale, x[c + 2] * inv_scale, x[c + 3] * inv_scale);
+            }
+#pragma unroll
+            for (int c = 0; c < CH; c += 4) {
+                s0 += x[c]; s1 += x[c + 1]; s2 += x[c + 2]; s3 += x[c + 3];
+                q0 = fmaf(x[c], x[c], q0); q1 = fmaf(x[c + 1], x[c + 1], q1); q2 = fmaf(x[c + 2], x[c + 2], q2); q3 = fmaf(x[c + 3], x[c + 3], q3);
+            }
+        }
+        my_x[0] = (s0 + s1) + (s2 + s3);
+        my_x[32] = (q0 + q1) + (q2 + q3);
+        named_bar_sync(1 + q, 32 * NS);
+        const float mean = xsum(0) * inv_h;
+        const float var = fmaxf(fmaf(-mean, mean, xsum(1) * inv_h), 0.0f) * inv_scale * inv_scale;
+#else
         // pass 1: mean (model.py:55-56)
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll 1
@@ -283,6 +307,7 @@ __device__ __forceinline__ void tce_epilogue_loop_wide(const EncodeArgs &a, floa
         my_x[32] = (s0 + s1) + (s2 + s3);
         named_bar_sync(1 + q, 32 * NS);
         const float var = xsum(1) * inv_h * inv_scale * inv_scale;
+#endif
         const float nrm = inv_scale / sqrtf(var + C2V_LN_EPS);
         const float shift = -mean * nrm;
         // pass 3: tanh (model.py:57), dropout (:60-61), score h.a (:92-93); h goes back into the accumulator

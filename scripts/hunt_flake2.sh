@@ -12,7 +12,7 @@ done
 echo "$TAG single-test: $fail / $total failed, $(( $(date +%s) - t0 )) s"
 ffail=0
 for i in $(seq 1 $NFULL); do
-    python -m pytest tests -q -m gpu -p no:cacheprovider > $OUT/$TAG.full$i.log 2>&1 || { ffail=$((ffail+1)); echo "FAIL full suite run $i: $(grep -E 'FAILED|failed' $OUT/$TAG.full$i.log | head -3)"; continue; }
+    python -m pytest tests -q -m gpu -p no:cacheprovider > $OUT/$TAG.full$i.log 2>&1 || { ffail=$((ffail+1)); echo "FAIL full suite run $i: $(grep -E "FAILED|failed" $OUT/$TAG.full$i.log | head -3)"; continue; }
     rm -f $OUT/$TAG.full$i.log
 done
 echo "$TAG full suite: $ffail / $NFULL failed, $(( $(date +%s) - t0 )) s"
