@@ -44,6 +44,11 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
                            cudaStream_t st, const float *x_stash);
 size_t encode_backward_workspace_bytes(const c2v_dims *d, int B, int L);
 bool label_tcgen05_shape_ok(const c2v_dims *d);
+bool label_backward_tc_ok(const c2v_dims *d);
+int label_w_image(const c2v_dims *d, const float *Wout, int B, void *ws, size_t ws_bytes, bool reuse_prep, cudaStream_t st,
+                  const uint8_t **img, const float **hdr, unsigned **scratch);
+int launch_label_backward_tc(const c2v_dims *d, const float *cv, const float *G, int B, const uint8_t *w_img,
+                             const float *w_hdr, float *d_cv, float *d_w, float *d_b, unsigned *scratch, cudaStream_t st);
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B);
 
 // ---- profiling hook (c2v_profile_enable / c2v_profile_read) ----------------------------
@@ -492,6 +497,35 @@ int c2v_label_backward(const c2v_dims *d, const c2v_params *p, const float *code
     if (rc != C2V_OK) return rc;
     if (d_output_bias) rc = launch_colsum(d_outputs, B, C, d_output_bias, st);
     return rc;
+}
+
+int c2v_label_backward_ws(const c2v_dims *d, const c2v_params *p, const float *code_vector, const float *d_outputs,
+                          int32_t B, float *d_code_vector, float *d_output_weight, float *d_output_bias, void *workspace,
+                          size_t workspace_bytes, int32_t algo, void *stream)
+{
+    if (!dims_ok(d)) return C2V_EINVAL;
+    if (!p || !p->output_weight || !code_vector || !d_outputs || B < 1) {
+        set_error("c2v_label_backward_ws: bad argument");
+        return C2V_EINVAL;
+    }
+    const int base_algo = algo & 0xff;
+    const char *env = getenv("C2V_LABEL_BACKWARD");
+    const bool tc = base_algo != C2V_ALGO_FFMA && workspace != nullptr && label_backward_tc_ok(d) &&
+                    (d_output_weight != nullptr || d_output_bias == nullptr) && !(env && !strcmp(env, "ffma"));
+    if (!tc) {
+        if (base_algo == C2V_ALGO_TCGEN05) {
+            set_error("tensor-core label backward needs a label workspace, encode_size %% 4 == 0 and <= 256");
+            return C2V_EUNSUPPORTED;
+        }
+        return c2v_label_backward(d, p, code_vector, d_outputs, B, d_code_vector, d_output_weight, d_output_bias, stream);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint8_t *img = nullptr; const float *hdr = nullptr; unsigned *scratch = nullptr;
+    int rc = label_w_image(d, p->output_weight, B, workspace, workspace_bytes, (algo & C2V_FLAG_REUSE_PREP) != 0, st, &img, &hdr,
+                           &scratch);
+    if (rc != C2V_OK) return rc;
+    return launch_label_backward_tc(d, code_vector, d_outputs, B, img, hdr, d_code_vector, d_output_weight, d_output_bias,
+                                    scratch, st);
 }
 
 size_t c2v_encode_backward_workspace_bytes(const c2v_dims *d, int32_t B, int32_t L)

@@ -494,6 +494,34 @@ int launch_label_tcgen05_ex(const c2v_dims *d, const float *cv, int B, const flo
                             float *out, long long *argmax, float *maxval, void *ws, size_t ws_bytes, bool reuse_prep,
                             cudaStream_t st, const LabelLossArgs *la);
 
+// The cached W_out image of a label workspace (built here unless reuse_prep): what the tensor-core label backward streams.
+int label_w_image(const c2v_dims *d, const float *Wout, int B, void *ws, size_t ws_bytes, bool reuse_prep, cudaStream_t st,
+                  const uint8_t **img, const float **hdr, unsigned **scratch)
+{
+    if (!label_tcgen05_shape_ok(d) || !ws || ws_bytes < label_tcgen05_workspace_bytes(d, B)) {
+        set_error("label backward: workspace missing or too small");
+        return C2V_EWORKSPACE;
+    }
+    const int H = d->encode, nkb = (H + 63) / 64;
+    const long long C = d->label_count;
+    uint8_t *p = static_cast<uint8_t *>(ws);
+    float *h = reinterpret_cast<float *>(p);
+    unsigned *mxbits = reinterpret_cast<unsigned *>(p + 256);
+    uint8_t *imgB = p + 1024;
+    if (!reuse_prep) {
+        int dev = 0, sms = 0;
+        C2V_CUDA_OK(cudaGetDevice(&dev));
+        C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        C2V_CUDA_OK(cudaMemsetAsync(mxbits, 0, 4, st));
+        absmax_kernel<<<sms * 4, 256, 0, st>>>(Wout, C * H, mxbits);
+        C2V_LAUNCH_OK("absmax_kernel");
+        split_rows_kernel<<<sms * 8, 256, 0, st>>>(Wout, C, H, nkb, mxbits, imgB, h, nullptr, 0);
+        C2V_LAUNCH_OK("split_rows_kernel");
+    }
+    *img = imgB; *hdr = h; *scratch = reinterpret_cast<unsigned *>(p + 768);
+    return C2V_OK;
+}
+
 int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float *Wout, const float *bias,
                          float *out, long long *argmax, float *maxval, void *ws, size_t ws_bytes, bool reuse_prep,
                          cudaStream_t st)

@@ -322,19 +322,30 @@ def loss_argmax(outputs, label=None, want_grad=False):
     return loss, am, mx, dout
 
 
-def label_backward(dims, params, cv, d_out, need_cv=True, need_w=True, need_b=True):
+def label_backward(dims, params, cv, d_out, need_cv=True, need_w=True, need_b=True, algo=_lib.ALGO_AUTO, cache=None,
+                   weight=None):
+    """backward of model.py:83 -> (d_code_vector, d_output_weight, d_output_bias).  With the label PrepCache of the
+    forward (cache + weight) the two contractions run on the tensor cores and stream the cached W_out image."""
     lib = _lib.load()
     B = cv.shape[0]
     dev = cv.device
     with torch.cuda.device(dev):
         d_cv = torch.empty_like(cv) if need_cv else None
-        d_w = _empty((dims.label_count, dims.encode), torch.float32, dev) if need_w else None
+        d_w = _empty((dims.label_count, dims.encode), torch.float32, dev) if (need_w or need_b) else None
         d_b = _empty((dims.label_count,), torch.float32, dev) if need_b else None
         cv = _f32c(cv, "code_vector"); d_out = _f32c(d_out, "d_outputs")
-        rc = lib.c2v_label_backward(ctypes.byref(dims), ctypes.byref(params), _ptr(cv),
-                                    _ptr(d_out), B, _ptr(d_cv), _ptr(d_w), _ptr(d_b), _stream(dev))
-        _lib.check(rc, "c2v_label_backward")
-    return d_cv, d_w, d_b
+        if cache is not None and weight is not None:
+            nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
+            ws, reuse = cache.get(nbytes, dev, weight)
+            flags = int(algo) | (REUSE_PREP if reuse else 0)
+            rc = lib.c2v_label_backward_ws(ctypes.byref(dims), ctypes.byref(params), _ptr(cv), _ptr(d_out), B, _ptr(d_cv),
+                                           _ptr(d_w), _ptr(d_b), _ptr(ws), ws.numel(), flags, _stream(dev))
+            _lib.check(rc, "c2v_label_backward_ws")
+        else:
+            rc = lib.c2v_label_backward(ctypes.byref(dims), ctypes.byref(params), _ptr(cv),
+                                        _ptr(d_out), B, _ptr(d_cv), _ptr(d_w), _ptr(d_b), _stream(dev))
+            _lib.check(rc, "c2v_label_backward")
+    return d_cv, (d_w if need_w else None), d_b
 
 
 def encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p=0.0, training=False,

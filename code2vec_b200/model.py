@@ -76,7 +76,7 @@ class _LabelFn(torch.autograd.Function):
             algo = int(algo) | CF.NO_PDL            # the calls that feed autograd use plain stream-ordered launches
         out = CF.label_logits(dims, params, cv, algo, cache=cache, weight=w_out)
         ctx.save_for_backward(cv, w_out)
-        ctx.dims = dims
+        ctx.dims, ctx.cache, ctx.algo = dims, cache, int(algo) & 0xff
         return out
 
     @staticmethod
@@ -84,7 +84,8 @@ class _LabelFn(torch.autograd.Function):
         cv, w_out = ctx.saved_tensors
         params = CF.make_params(None, None, None, None, None, None, w_out, None)
         d_cv, d_w, d_b = CF.label_backward(ctx.dims, params, cv, d_out, ctx.needs_input_grad[0],
-                                           ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+                                           ctx.needs_input_grad[1], ctx.needs_input_grad[2], algo=ctx.algo, cache=ctx.cache,
+                                           weight=w_out)
         return d_cv, d_w, d_b, None, None, None
 
 
@@ -132,7 +133,7 @@ class _LabelLossFn(torch.autograd.Function):
         d_out = CF.label_dlogits(ctx.dims, params, cv, label, lse, 1.0 / B, scale_device=d_loss.reshape(1),
                                  algo=ctx.algo, cache=ctx.cache, weight=w_out)
         d_cv, d_w, d_b = CF.label_backward(ctx.dims, params, cv, d_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                           ctx.needs_input_grad[2])
+                                           ctx.needs_input_grad[2], algo=int(ctx.algo) & 0xff, cache=ctx.cache, weight=w_out)
         return d_cv, d_w, d_b, None, None, None, None
 
 

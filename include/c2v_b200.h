@@ -215,6 +215,14 @@ int c2v_loss_argmax(const float *outputs, const int64_t *label, int32_t B, int64
 int c2v_label_backward(const c2v_dims *d, const c2v_params *p, const float *code_vector,
                        const float *d_outputs, int32_t B, float *d_code_vector,
                        float *d_output_weight, float *d_output_bias, void *stream);
+/* c2v_label_backward on the tensor cores (dW_out = d_out^T . cv with the column sums d_b folded in, d_cv = d_out . W_out
+ * streaming the cached W_out image): `workspace` is the label workspace of c2v_label_logits* for this weight
+ * (C2V_FLAG_REUSE_PREP in `algo` = its image is current, e.g. the forward of the same step built it).  Falls back to
+ * c2v_label_backward (CUDA cores) when workspace == NULL, encode_size % 4 != 0 or > 256, or algo == C2V_ALGO_FFMA. */
+int c2v_label_backward_ws(const c2v_dims *d, const c2v_params *p, const float *code_vector, const float *d_outputs,
+                          int32_t B, float *d_code_vector, float *d_output_weight, float *d_output_bias, void *workspace,
+                          size_t workspace_bytes, int32_t algo, void *stream);
+
 /* Encode: gradients of every encode parameter given d_code_vector [B,H] and
  * (optionally, may be NULL) d_attention [B,L]; formulas in DESIGN.md "Backward".
  * Recomputes the forward per context row (nothing but code_vector / attention is

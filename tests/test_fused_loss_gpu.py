@@ -96,3 +96,29 @@ def test_an_out_of_range_label_makes_the_loss_nan():
     params = CF.make_params(None, None, None, None, None, None, cuda(W), cuda(b))
     loss = CF.label_loss(dims, params, cuda(cv), cuda(lab))[0]
     assert np.isnan(loss.item())
+
+
+# ---- label backward on the tensor cores (c2v_label_backward_ws) vs fp64 matrix products ------------------------------
+@pytest.mark.parametrize("B,C,H", [(7, 11, 128), (130, 1000, 128), (64, 4097, 100), (33, 260, 256), (1024, 8192, 128),
+                                    (200, 777, 64), (5, 3, 4)])
+@pytest.mark.parametrize("gscale", [1.0, 1e-6])
+def test_label_backward_tensor_cores(B, C, H, gscale):
+    rng = np.random.default_rng(B + C)
+    cv, W, b, lab = _case(rng, B, C, H, 3.0)
+    G = (rng.standard_normal((B, C)) * gscale).astype(np.float32)
+    G[rng.random((B, C)) < 0.3] = 0.0
+    dims = CF.make_dims(10, 10, C, H, H, H)
+    w_t = cuda(W)
+    params = CF.make_params(None, None, None, None, None, None, w_t, cuda(b))
+    cache = CF.PrepCache()
+    ref_dcv = G.astype(np.float64) @ W.astype(np.float64)
+    ref_dw = G.astype(np.float64).T @ cv.astype(np.float64)
+    ref_db = G.astype(np.float64).sum(0)
+    for attempt in ("fresh image", "image reused"):               # second call: C2V_FLAG_REUSE_PREP path
+        d_cv, d_w, d_b = CF.label_backward(dims, params, cuda(cv), cuda(G), cache=cache, weight=w_t)
+        for got, ref, name in ((d_cv, ref_dcv, "d_cv"), (d_w, ref_dw, "d_w"), (d_b, ref_db, "d_b")):
+            tol = 2e-5 * max(float(np.abs(ref).max()), 1e-30)
+            assert np.abs(got.cpu().numpy() - ref).max() <= tol, (name, attempt)
+    # and the CUDA-core path gives the same answer (no workspace)
+    d_cv2, d_w2, d_b2 = CF.label_backward(dims, params, cuda(cv), cuda(G))
+    assert np.abs(d_cv2.cpu().numpy() - ref_dcv).max() <= 2e-5 * max(float(np.abs(ref_dcv).max()), 1e-30)
