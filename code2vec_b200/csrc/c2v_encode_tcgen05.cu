@@ -133,6 +133,7 @@ int launch_split_w_tcgen05(const c2v_dims *d, const float *W, EncodeWorkspace &w
 
 // ------------------------------------------------------------------------------------
 // the kernel
+#ifdef C2V_EXPERIMENTS   // K1b (superseded): built only with C2V_NVCC_EXTRA=-DC2V_EXPERIMENTS
 // ------------------------------------------------------------------------------------
 struct ProducerIdx { long long s, p, e; };
 
@@ -333,6 +334,8 @@ encode_tcgen05_kernel(const EncodeArgs a)
 }
 
 
+#endif  // C2V_EXPERIMENTS
+
 bool encode_tma_available();
 int launch_encode_tma(const EncodeArgs &a, cudaStream_t st);
 int launch_encode_cpa(const EncodeArgs &a, cudaStream_t st);
@@ -349,6 +352,9 @@ int launch_encode_tm(const EncodeArgs &a, cudaStream_t st);
 // Measurements: profiles/README.md.
 int launch_encode_tcgen05(const EncodeArgs &a, cudaStream_t st)
 {
+#ifndef C2V_EXPERIMENTS
+    return launch_encode_tm(a, st);       // product builds ship K1e only; the older variants need -DC2V_EXPERIMENTS
+#else
     const char *which = getenv("C2V_ENCODE_KERNEL");
     if (a.Et != tc::E || a.H != tc::H) which = nullptr;        // the older variants are 128/128/128 only
     if (which && !strcmp(which, "tma") && encode_tma_available()) return launch_encode_tma(a, st);
@@ -367,6 +373,7 @@ int launch_encode_tcgen05(const EncodeArgs &a, cudaStream_t st)
     kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(b);
     C2V_LAUNCH_OK("encode_tcgen05_kernel");
     return C2V_OK;
+#endif
 }
 
 }  // namespace c2v

@@ -51,7 +51,7 @@ __device__ __forceinline__ void tce_tile_body(const EncodeArgs &a, const float *
         for (int s = 0; s < NS; ++s) t += qx[(s * 3 + slot) * 32];
         return t;
     };
-#ifdef TCE_ONEPASS_LN
+#ifndef TCE_TWOPASS_LN
     // LayerNorm (model.py:55-56), one pass: sum and sum of squares together (one exchange between the slices instead of
     // two); padding columns are exactly 0 and drop out of both.  var = E[x^2] - mean^2 in fp32: relative error
     // ~2^-24 (1 + mean^2 / var), far inside the 1e-4 budget for the row statistics of c . W^T.
@@ -252,7 +252,7 @@ __device__ __forceinline__ void tce_epilogue_loop_wide(const EncodeArgs &a, floa
         mbar_wait(bar_tfull, (uint32_t)tl & 1u, status);
         tc_fence_after();
         float x[CH];
-#ifdef TCE_ONEPASS_LN
+#ifndef TCE_TWOPASS_LN
         // pass 1: sum and sum of squares together (model.py:55-56; see tce_tile_body): one walk over the accumulator less
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll 1

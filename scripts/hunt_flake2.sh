@@ -6,7 +6,7 @@ export C2V_LIB=$PWD/$LIB C2V_POISON=1
 fail=0; total=0; t0=$(date +%s)
 for r in $(seq 1 $NPAR); do
     pids=()
-    for j in 1 2 3 4; do ( python scripts/flake_once.py > $OUT/$TAG.p${r}_$j.log 2>&1 || { echo "FAIL $TAG.p${r}_$j"; exit 1; }; rm -f $OUT/$TAG.p${r}_$j.log ) & pids+=($!); done
+    for j in 1 2 3 4; do ( python scripts/${FLAKE_SCRIPT:-flake_once.py} > $OUT/$TAG.p${r}_$j.log 2>&1 || { echo "FAIL $TAG.p${r}_$j"; exit 1; }; rm -f $OUT/$TAG.p${r}_$j.log ) & pids+=($!); done
     for p in "${pids[@]}"; do wait $p || fail=$((fail+1)); total=$((total+1)); done
 done
 echo "$TAG single-test: $fail / $total failed, $(( $(date +%s) - t0 )) s"
