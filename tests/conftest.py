@@ -42,3 +42,23 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden_loader():
     return load_golden
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _warm_up_aten_cpu_reference():
+    """The torch-CPU restatement (oracle.torch_forward) is the reference of several tests.  On the many-core GPU-box host
+    the first fp32 evaluation of its LayerNorm + autograd in a fresh process was found to be occasionally off by ~1e-4
+    relative (profiles/r2_flake_root_cause.txt); every later evaluation in the same process is right.  Run it once, on
+    sizes that exercise the parallel paths, before any test uses it as a reference."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    for _ in range(2):
+        x = torch.randn(640, 128, generator=g, requires_grad=True)
+        w = torch.randn(128, generator=g, requires_grad=True)
+        b = torch.randn(128, generator=g, requires_grad=True)
+        emb = torch.randn(300, 128, generator=g, requires_grad=True)
+        idx = torch.randint(0, 300, (640,), generator=g)
+        y = torch.tanh(F.layer_norm(F.linear(F.embedding(idx, emb) + x, torch.eye(128)), (128,), w, b, 1e-5))
+        (y.sum() + F.softmax(y, 1).square().sum()).backward()
+    yield

@@ -36,6 +36,33 @@ def test_gradients_match_reference_autograd(name, algo):
         assert np.abs(g - rec["grads"][k]).max() <= _tol(rec["grads"][k]), k
 
 
+def _fp64_reference_gradients(p, starts, paths, ends, label, wa, wc):
+    """fp64 evaluation of model.py:44-88 + the test loss with LayerNorm written out in elementwise ops.
+    Why not `oracle.torch_forward` in fp32 here (what round 1 did): on the 128-thread GPU-box host the FIRST fp32
+    ATen-CPU evaluation in a fresh process is occasionally off by ~1e-4 relative (always in LayerNorm's weight gradient,
+    sometimes in everything downstream); recomputed in the same process it is right, and the CUDA gradients agreed with
+    fp64 to 0.08 x tolerance in every such run (profiles/r2_flake_root_cause.txt: 7 of 240 fresh processes).  That --
+    not a kernel -- was the "intermittent gradient mismatch" of round 1."""
+    dt = torch.float64
+    tp = {k: torch.from_numpy(v).to(dt).requires_grad_(True) for k, v in p.items()}
+    s, pp, e = (torch.from_numpy(a) for a in (starts, paths, ends))
+    H = p["input_linear.weight"].shape[0]
+    c = torch.cat((F.embedding(s, tp["terminal_embedding.weight"]), F.embedding(pp, tp["path_embedding.weight"]),
+                   F.embedding(e, tp["terminal_embedding.weight"])), 2)                       # model.py:48-51
+    x = F.linear(c, tp["input_linear.weight"])                                               # model.py:54
+    xv = x.view(-1, H)
+    mu = xv.mean(1, keepdim=True); var = xv.var(1, unbiased=False, keepdim=True)
+    y = (xv - mu) / torch.sqrt(var + 1e-5) * tp["input_layer_norm.weight"] + tp["input_layer_norm.bias"]   # model.py:55-56
+    h = torch.tanh(y).view(x.shape)                                                          # model.py:57
+    mask = (s > 0).to(dt)                                                                    # model.py:64
+    z = (h * tp["attention_parameter"]).sum(2) * mask + (1 - mask) * (-3.4e38)               # model.py:92-93
+    att = F.softmax(z, 1)                                                                    # model.py:96
+    cv = (h * att.unsqueeze(-1)).sum(1)                                                      # model.py:68-69
+    out = F.linear(cv, tp["output_linear.weight"], tp["output_linear.bias"])                 # model.py:83
+    ((att * torch.from_numpy(wa).to(dt)).sum() + (cv * torch.from_numpy(wc).to(dt)).sum() + 0.1 * out.square().sum()).backward()
+    return {k: v.grad.numpy() for k, v in tp.items()}, (out.detach().numpy(), cv.detach().numpy(), att.detach().numpy())
+
+
 def test_gradients_with_attention_in_the_loss():
     from oracle import oracle
     rng = np.random.default_rng(5)
@@ -44,11 +71,11 @@ def test_gradients_with_attention_in_the_loss():
     starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
     starts[3, :] = 0                                       # all-pad bag: PAD row 0 does get gradient
     wa = rng.standard_normal((B, L)).astype(np.float32); wc = rng.standard_normal((B, H)).astype(np.float32)
-    # reference gradients: torch-CPU autograd over the pinned restatement
-    tp = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in p.items()}
-    out, cv, att = oracle.torch_forward(tp, torch.from_numpy(starts), torch.from_numpy(paths), torch.from_numpy(ends),
-                                        torch.from_numpy(label))
-    ((att * torch.from_numpy(wa)).sum() + (cv * torch.from_numpy(wc)).sum() + 0.1 * out.square().sum()).backward()
+    ref_grads, (ref_out, ref_cv, ref_att) = _fp64_reference_gradients(p, starts, paths, ends, label, wa, wc)
+    # the fp64 evaluation is the pinned restatement: same forward as oracle.torch_forward (which is pinned to the reference)
+    o32 = oracle.torch_forward({k: torch.from_numpy(v) for k, v in p.items()}, torch.from_numpy(starts),
+                               torch.from_numpy(paths), torch.from_numpy(ends), torch.from_numpy(label))
+    assert np.abs(o32[0].numpy() - ref_out).max() <= 2e-5 and np.abs(o32[2].numpy() - ref_att).max() <= 2e-6
     rec = {"opt": {"T": T, "P": P, "C": C, "Et": E, "Ep": E, "H": H}, "params": p}
 
     m = model_from_golden(rec).train()
@@ -56,8 +83,9 @@ def test_gradients_with_attention_in_the_loss():
     ((att2 * cuda(wa)).sum() + (cv2 * cuda(wc)).sum() + 0.1 * out2.square().sum()).backward()
     got = dict(m.named_parameters())
     bad = {}
+    assert np.abs(cv2.detach().cpu().numpy() - ref_cv).max() <= 1e-5 and np.abs(att2.detach().cpu().numpy() - ref_att).max() <= 1e-5
     for k in KEYS:
-        ref = tp[k].grad.numpy()
+        ref = ref_grads[k]
         g = got[k].grad.cpu().numpy()
         d = np.abs(g - ref)
         err = float(np.nanmax(d)) if not np.isnan(d).all() else float("nan")
@@ -66,7 +94,7 @@ def test_gradients_with_attention_in_the_loss():
             bad[k] = {"err": err, "tol": _tol(ref), "n_bad": int((~(d <= _tol(ref))).sum()), "n_nan": int(np.isnan(g).sum()),
                       "at": tuple(int(i) for i in idx), "got": float(g[idx]), "ref": float(ref[idx])}
     pad_grad = float(np.abs(got["terminal_embedding.weight"].grad[0].cpu().numpy()).max())
-    # strict: no retry (round 1 repeated this comparison once after an intermittent miss)
+    # strict, no retry: the round-1 intermittent miss was the fp32 CPU reference, not the kernels
     assert not bad, bad
     assert pad_grad > 0
 
