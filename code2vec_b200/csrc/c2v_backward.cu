@@ -252,7 +252,7 @@ backward_rows_kernel(const EncodeArgs a, const BackwardArgs b, const int Hs)
                         if (c < Et) dst = b.g_emb_t + (size_t)sidx[r] * Et + c;
                         else if (c < Et + Ep) dst = b.g_emb_p + (size_t)sidx[TM + r] * Ep + (c - Et);
                         else dst = b.g_emb_t + (size_t)sidx[2 * TM + r] * Et + (c - Et - Ep);
-                        atomicAdd(reinterpret_cast<float4 *>(dst), make_float4(v0, v1, v2, v3));
+                        red_add_v4(dst, make_float4(v0, v1, v2, v3));
                     } else {
                         const float vv[4] = {v0, v1, v2, v3};
                         for (int q = 0; q < 4; ++q) {

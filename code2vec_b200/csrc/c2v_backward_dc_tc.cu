@@ -253,7 +253,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                         for (int j = 0; j < 32; j += 4) {
                             const float v0 = v[j] * inv, v1 = v[j + 1] * inv, v2 = v[j + 2] * inv, v3 = v[j + 3] * inv;
                             if (c * 32 + j < a.Et && (v0 != 0.0f || v1 != 0.0f || v2 != 0.0f || v3 != 0.0f))   // padded contexts: dx == 0
-                                atomicAdd(reinterpret_cast<float4 *>(dst + c * 32 + j), make_float4(v0, v1, v2, v3));
+                                red_add_v4(dst + c * 32 + j, make_float4(v0, v1, v2, v3));
                         }
                     }
                 }

@@ -226,7 +226,7 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     if (d0 + j < E)
-                        atomicAdd(reinterpret_cast<float4 *>(dst + sv * E + d0 + j), make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv));
+                        red_add_v4(dst + sv * E + d0 + j, make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv));
             }
         }
         tc_fence_before();

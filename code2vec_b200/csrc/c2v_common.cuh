@@ -185,6 +185,13 @@ __device__ __forceinline__ float dropout_mask_at(unsigned long long seed, long l
     return dropout_mul(w, p, scale);
 }
 
+// 128-bit reduction without a return value (REDG.E.ADD.F32x4): the scatter-add of gradient rows needs no old value, and
+// atomicAdd(float4 *) compiles to ATOMG (the returning form) even when the result is dropped.
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));

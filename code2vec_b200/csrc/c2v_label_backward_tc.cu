@@ -466,7 +466,7 @@ label_dcv_tc_kernel(const float *__restrict__ G, int B, long long C, int H, int 
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             if (ch * 32 + j < H)
-                                atomicAdd(reinterpret_cast<float4 *>(dst + j), make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv));
+                                red_add_v4(dst + j, make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv));
                     }
                 }
             }

@@ -312,6 +312,8 @@ class ShardedFlatAdam:
 
 def ddp_step(model, optimizer, bucket, starts, paths, ends, label, loss_fn):
     """One training step of main.py:171-175 on this rank's shard of the global batch."""
+    if isinstance(optimizer, (ShardedFlatAdam, FlatAdam)) and hasattr(model, "fuse_grad_accumulation"):
+        model.fuse_grad_accumulation = True                  # .grad are persistent views into a flat bucket: accumulate in place
     if isinstance(optimizer, ShardedFlatAdam):               # reduction + optimizer + broadcast are one kernel per rank
         if loss_fn is None:                                  # fused loss: the [b, C] logits are never written
             loss = model.forward_loss(starts, paths, ends, label)[0]

@@ -59,9 +59,25 @@ class _EncodeFn(torch.autograd.Function):
                   "ln_weight": ln_g.shape, "ln_bias": ln_b.shape, "attention": attn.shape}
         if d_cv is None:
             d_cv = torch.zeros_like(cv)
+        # Fused gradient accumulation (opt-in, Code2Vec.fuse_grad_accumulation; what ddp_step switches on for the flat
+        # optimizers): the embedding-table and input_linear gradients -- 99.9 % of the bytes -- are scatter-added straight into
+        # the existing dense .grad buffers instead of into fresh zero-filled tensors that autograd would then add to .grad
+        # (at cfg2: a 360 MB fill plus a 1.1 GB read-modify-write per step).  Autograd gets None for those three inputs.
+        big = (("terminal_embedding", emb_t), ("path_embedding", emb_p), ("input_linear", W))
+        fuse = bool(getattr(ctx.cache, "fuse_grad_accumulation", False)) and all(
+            t.grad is not None and t.grad.dtype == torch.float32 and t.grad.is_contiguous() and t.grad.shape == t.shape
+            and t.grad.device == t.device for _, t in big)
+        grads_out = None
+        if fuse:
+            grads_out = {k: t.grad for k, t in big}
+            for k in ("ln_weight", "ln_bias", "attention"):
+                grads_out[k] = torch.empty(shapes[k], dtype=torch.float32, device=cv.device)   # overwritten by the kernels
         g = CF.encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p, training, seed,
-                               x_stash=ctx.x_stash)
+                               grads_out=grads_out, x_stash=ctx.x_stash)
         ctx.x_stash = None
+        if fuse:
+            return (None, None, None, g["ln_weight"], g["ln_bias"], g["attention"], None, None, None, None, None, None,
+                    None, None, None)
         return (g["terminal_embedding"], g["path_embedding"], g["input_linear"], g["ln_weight"], g["ln_bias"],
                 g["attention"], None, None, None, None, None, None, None, None, None)
 
@@ -172,6 +188,9 @@ class Code2Vec(nn.Module):
         # persistent workspaces: the hi/lo split images of input_linear / output_linear are rebuilt
         # only when the optimizer changed the weights (tracked by the tensors' version counters)
         self._enc_cache = CF.PrepCache(mirror_errors=True)
+        # True: the backward adds the table / input_linear gradients directly into the parameters' existing .grad buffers
+        # (see _EncodeFn.backward); needs dense fp32 .grad tensors to exist before the backward, e.g. a flat gradient bucket
+        self.fuse_grad_accumulation = False
         self._lab_cache = CF.PrepCache()
 
     # -- helpers ---------------------------------------------------------------------------
@@ -194,6 +213,7 @@ class Code2Vec(nn.Module):
 
     def forward(self, starts, paths, ends, label):
         self._enc_cache.raise_deferred()
+        self._enc_cache.fuse_grad_accumulation = self.fuse_grad_accumulation
         option = self.option
         dims = self._dims()
         training = self.training and self.input_dropout is not None
@@ -228,6 +248,7 @@ class Code2Vec(nn.Module):
         if self.option.angular_margin_loss:
             raise NotImplementedError("forward_loss() needs the plain label head")
         self._enc_cache.raise_deferred()
+        self._enc_cache.fuse_grad_accumulation = self.fuse_grad_accumulation
         dims = self._dims()
         training = self.training and self.input_dropout is not None
         drop_p = float(self.option.dropout_prob) if training else 0.0

@@ -6,7 +6,7 @@ import torch, torch.nn.functional as F
 from torch.profiler import profile, ProfilerActivity
 from bench import WORKLOADS, synth_params, synth_pool
 from code2vec_b200.model import Code2Vec
-from code2vec_b200.distributed import FlatGradBucket, ddp_step
+from code2vec_b200.distributed import ShardedFlatAdam, ddp_step
 w = dict(WORKLOADS["cfg2"]); dev = torch.device("cuda:0")
 p = synth_params(w, dev); s, pth, e, lab = synth_pool(w, 8, dev, 1)
 B = w["B"]
@@ -14,8 +14,8 @@ o = types.SimpleNamespace(terminal_count=w["T"], path_count=w["P"], label_count=
                           path_embed_size=128, encode_size=128, dropout_prob=0.25, angular_margin_loss=False,
                           angular_margin=0.5, inverse_temp=30.0, device=dev)
 m = Code2Vec(o); m.load_state_dict(p); m = m.to(dev).train()
-bucket = FlatGradBucket(m.parameters()); opt = torch.optim.Adam(m.parameters(), lr=0.01)
-lf = lambda o_, l_: F.nll_loss(F.log_softmax(o_, dim=1), l_)
+opt = ShardedFlatAdam(m.parameters(), lr=0.01); bucket = None
+lf = None if os.environ.get("FUSED_LOSS", "1") == "1" else (lambda o_, l_: F.nll_loss(F.log_softmax(o_, dim=1), l_))
 for i in range(3): ddp_step(m, opt, bucket, s[:B], pth[:B], e[:B], lab[:B], lf)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:

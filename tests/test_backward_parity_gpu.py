@@ -261,3 +261,29 @@ def test_angular_head_gradients_match_reference_autograd(name):
     for k, p in m.named_parameters():
         ref = rec["grads"][k]
         assert np.abs(p.grad.cpu().numpy() - ref).max() <= _tol(ref), k
+
+
+@pytest.mark.parametrize("name", ["grad_cfg2", "grad_cfg1", "grad_odd"])
+def test_fused_grad_accumulation_equals_autograd_accumulation(name):
+    """Code2Vec.fuse_grad_accumulation: the table / input_linear gradients are added straight into existing .grad buffers
+    (what ddp_step uses with the flat optimizers) -- same result as letting autograd accumulate fresh gradient tensors."""
+    rec = load_golden(name)
+    s, p, e, lab = (cuda(rec[k]) for k in ("starts", "paths", "ends", "label"))
+    res = []
+    for fuse in (False, True):
+        torch.manual_seed(3)
+        m = model_from_golden(rec).train()
+        for prm in m.parameters():                       # pre-existing, non-zero gradients: accumulation, not overwrite
+            prm.grad = torch.randn_like(prm) * 0.01
+        before = {k: v.grad.clone() for k, v in m.named_parameters()}
+        m.fuse_grad_accumulation = fuse
+        ptrs = {k: v.grad.data_ptr() for k, v in m.named_parameters()}
+        out, cv, att = m.forward(s, p, e, lab)
+        F.nll_loss(F.log_softmax(out, dim=1), lab).backward()
+        for k, v in m.named_parameters():
+            assert v.grad.data_ptr() == ptrs[k], k       # .grad buffers stay where they are (flat-bucket views survive)
+        res.append({k: (v.grad - before[k]).cpu().numpy() for k, v in m.named_parameters()})
+    for k in res[0]:
+        ref = rec["grads"][k]
+        assert np.abs(res[1][k] - ref).max() <= _tol(ref) + 2e-8, k          # fused path vs the reference's autograd
+        assert np.abs(res[1][k] - res[0][k]).max() <= 2e-6 * max(1.0, float(np.abs(ref).max())) + 2e-8, k
