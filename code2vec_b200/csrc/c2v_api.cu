@@ -346,9 +346,13 @@ int c2v_label_logits_argmax(const c2v_dims *d, const c2v_params *p, const float 
                             size_t workspace_bytes, int32_t algo, void *stream)
 {
     if (!dims_ok(d)) return C2V_EINVAL;
-    if (!p || !p->output_weight || !code_vector || !outputs || B < 1 || d->label_count < 1) {
+    if (!p || !p->output_weight || !code_vector || B < 1 || d->label_count < 1 || (!outputs && !argmax && !maxval)) {
         set_error("c2v_label_logits_argmax: bad argument");
         return C2V_EINVAL;
+    }
+    if (!outputs && !c2v_label_loss_supported(d, B)) {       // arg-max without the logits needs the fused tensor-core epilogue
+        set_error("c2v_label_logits_argmax: outputs == NULL needs encode_size %% 4 == 0, <= 256 and B <= 2048");
+        return C2V_EUNSUPPORTED;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool reuse_prep = (algo & C2V_FLAG_REUSE_PREP) != 0;

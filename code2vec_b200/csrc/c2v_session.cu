@@ -125,9 +125,12 @@ int c2v_forward_host_async(c2v_session *s, const c2v_params *p, const int64_t *s
                                 q.ws_enc_bytes, base_algo | reuse, s->s_run);
     if (rc != C2V_OK) return rc;
     const bool want_head = outputs || pred_label || pred_score;
+    // the [B, C] logits are only materialised when the caller asked for them (or the fused arg-max cannot serve this shape):
+    // the predict surface (code vector, attention, arg-max, score) never writes them
+    float *logits_dst = (outputs || base_algo == C2V_ALGO_FFMA || !c2v_label_loss_supported(&s->dims, B)) ? q.d_out : nullptr;
     if (want_head) {
         if (!p->output_weight) { set_error("c2v_forward_host: output_weight is NULL"); return C2V_EINVAL; }
-        rc = c2v_label_logits_argmax(&s->dims, p, q.d_cv, B, q.d_out, pred_label ? (int64_t *)q.d_pred : nullptr,
+        rc = c2v_label_logits_argmax(&s->dims, p, q.d_cv, B, logits_dst, pred_label ? (int64_t *)q.d_pred : nullptr,
                                      pred_score ? q.d_score : nullptr, q.ws_lab, q.ws_lab_bytes,
                                      (base_algo == C2V_ALGO_FFMA ? C2V_ALGO_FFMA : C2V_ALGO_AUTO) | reuse, s->s_run);
         if (rc != C2V_OK) return rc;

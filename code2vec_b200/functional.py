@@ -170,14 +170,16 @@ def label_logits(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weight=None)
     return out
 
 
-def label_logits_argmax(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weight=None):
-    """model.py:83 + main.py:285 fused -> (outputs [B,C], argmax int64 [B], maxval [B])"""
+def label_logits_argmax(dims, params, cv, algo=_lib.ALGO_AUTO, cache=None, weight=None, want_logits=True):
+    """model.py:83 + main.py:285 fused -> (outputs [B,C] or None, argmax int64 [B], maxval [B])"""
     lib = _lib.load()
     _need_cuda(cv)
     B = cv.shape[0]
     dev = cv.device
+    if not want_logits and ((int(algo) & 0xff) == _lib.ALGO_FFMA or not label_loss_supported(dims, B)):
+        want_logits = True                      # the CUDA-core / B > 2048 paths take the arg-max from stored logits
     with torch.cuda.device(dev):
-        out = _empty((B, dims.label_count), torch.float32, dev)
+        out = _empty((B, dims.label_count), torch.float32, dev) if want_logits else None
         am = _empty((B,), torch.int64, dev)
         mx = _empty((B,), torch.float32, dev)
         nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)

@@ -282,5 +282,5 @@ class Code2Vec(nn.Module):
                                                    cache=self._enc_cache, weight=self.input_linear.weight)
         _, am, mx = CF.label_logits_argmax(dims, params, code_vector,
                                            _lib.ALGO_FFMA if self.algo == _lib.ALGO_FFMA else _lib.ALGO_AUTO,
-                                           cache=self._lab_cache, weight=self.output_linear.weight)
+                                           cache=self._lab_cache, weight=self.output_linear.weight, want_logits=False)
         return am, mx, code_vector, attention

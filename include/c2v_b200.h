@@ -194,7 +194,9 @@ int c2v_label_dlogits(const c2v_dims *d, const c2v_params *p, const float *code_
                       void *workspace, size_t workspace_bytes, int32_t algo, void *stream);
 /* Label logits + the prediction the reference takes from them (`torch.max(preds, dim=1)`,
  * main.py:285; first maximum wins) in one call: the argmax pass runs right behind the GEMM while the
- * [B,C] logits are still in L2.  argmax int64 [B], maxval fp32 [B] (either may be NULL). */
+ * [B,C] logits are still in L2.  argmax int64 [B], maxval fp32 [B] (either may be NULL).
+ * outputs == NULL (tensor-core path, B <= 2048: c2v_label_loss_supported): only the prediction is produced and the
+ * logits are never written -- what predict() and the host-buffer calls do when the caller does not ask for them. */
 int c2v_label_logits_argmax(const c2v_dims *d, const c2v_params *p, const float *code_vector, int32_t B,
                             float *outputs, int64_t *argmax, float *maxval, void *workspace,
                             size_t workspace_bytes, int32_t algo, void *stream);
