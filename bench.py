@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--train-steps", type=int, default=8, help="also time K training steps (0 = skip)")
     ap.add_argument("--train-unfused-loss", action="store_true", help="training leg: forward() + eager loss instead of forward_loss()")
+    ap.add_argument("--no-early-reduce", action="store_true", help="training leg: reduce all gradients after the backward (no overlap)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the ATen/cuBLAS eager comparator on this GPU")
     ap.add_argument("--transport", default="auto", choices=["auto", "nvls", "p2p", "nccl"],
                     help="gradient reduction of the training leg (ShardedFlatAdam)")
@@ -529,7 +530,8 @@ def main():
         model = Code2Vec(opt_ns, algo=args.algo)
         model.load_state_dict(p)
         model = model.to(dev).train()
-        optim = ShardedFlatAdam(model.parameters(), lr=0.01, betas=(0.9, 0.999), transport=args.transport)   # main.py:138
+        optim = ShardedFlatAdam(model.parameters(), lr=0.01, betas=(0.9, 0.999), transport=args.transport,   # main.py:138
+                                early=[] if args.no_early_reduce else [model.path_embedding.weight])
         # main.py:251-264: by default through Code2Vec.forward_loss (loss fused into the label GEMM, logits never written);
         # --train-unfused-loss: forward() + eager log_softmax + nll_loss on the [b, C] logits, like the reference's loop
         loss_fn = (lambda o_, l_: F.nll_loss(F.log_softmax(o_, dim=1), l_)) if args.train_unfused_loss else None
@@ -558,7 +560,7 @@ def main():
                  "loss": "forward + eager log_softmax/nll_loss" if args.train_unfused_loss else "fused into the label GEMM (forward_loss)",
                  "step": "forward(dropout .25) + mean NLL + backward + gradient reduction over the ranks + dense Adam "
                          "(optimizer state sharded 1/world; reduction + Adam + parameter broadcast = one kernel per rank)",
-                 "transport": optim.transport, "transport_calibration_ms": optim.calibration, "gradient_bytes": 4 * optim.numel, "loss_value": float(res[-1][1].item())}
+                 "early_region": len(optim.regions) > 1, "transport": optim.transport, "transport_calibration_ms": optim.calibration, "gradient_bytes": 4 * optim.numel, "loss_value": float(res[-1][1].item())}
         del model, optim
         torch.cuda.empty_cache()
 

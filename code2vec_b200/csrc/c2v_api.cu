@@ -41,7 +41,7 @@ int launch_colsum(const float *X, int B, long long C, float *out, cudaStream_t s
 int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeArgs &a, int B,
                            const float *cv, const float *attention, const float *d_cv,
                            const float *d_att, const c2v_grads *g, void *ws, size_t ws_bytes,
-                           cudaStream_t st, const float *x_stash);
+                           cudaStream_t st, const float *x_stash, int phase);
 size_t encode_backward_workspace_bytes(const c2v_dims *d, int B, int L);
 bool label_tcgen05_shape_ok(const c2v_dims *d);
 bool label_backward_tc_ok(const c2v_dims *d);
@@ -554,6 +554,17 @@ int c2v_encode_backward_stashed(const c2v_dims *d, const c2v_params *p, const in
                                 const float *x_stash, const float *d_code_vector, const float *d_attention,
                                 const c2v_grads *grads, void *workspace, size_t workspace_bytes, void *stream)
 {
+    return c2v_encode_backward_phased(d, p, starts, paths, ends, B, L, drop, code_vector, attention, x_stash, d_code_vector,
+                                      d_attention, grads, workspace, workspace_bytes, 0, stream);
+}
+
+int c2v_encode_backward_phased(const c2v_dims *d, const c2v_params *p, const int64_t *starts,
+                               const int64_t *paths, const int64_t *ends, int32_t B, int32_t L,
+                               const c2v_dropout *drop, const float *code_vector, const float *attention,
+                               const float *x_stash, const float *d_code_vector, const float *d_attention,
+                               const c2v_grads *grads, void *workspace, size_t workspace_bytes, int32_t phase, void *stream)
+{
+    if (phase < 0 || phase > 2) { set_error("c2v_encode_backward_phased: phase %d", phase); return C2V_EINVAL; }
     if (!dims_ok(d)) return C2V_EINVAL;
     if (!p || !starts || !paths || !ends || !code_vector || !attention || !d_code_vector || !grads ||
         !workspace || B < 1 || L < 1) {
@@ -582,7 +593,7 @@ int c2v_encode_backward_stashed(const c2v_dims *d, const c2v_params *p, const in
     }
     return launch_encode_backward(d, p, a, B, code_vector, attention, d_code_vector, d_attention,
                                   grads, workspace, workspace_bytes,
-                                  static_cast<cudaStream_t>(stream), x_stash);
+                                  static_cast<cudaStream_t>(stream), x_stash, phase);
 }
 
 }  // extern "C"

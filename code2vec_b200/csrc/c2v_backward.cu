@@ -30,7 +30,7 @@ bool backward_dw_tc_ok(const EncodeArgs &a);
 bool backward_dc_tc_ok(const EncodeArgs &a);
 size_t backward_dc_tc_workspace_bytes();
 int launch_backward_dc_tc(const EncodeArgs &a, const float *W, const float *dx, const unsigned *dx_absmax, void *ws,
-                          float *g_emb_t, float *g_emb_p, cudaStream_t st);
+                          float *g_emb_t, float *g_emb_p, cudaStream_t st, int sv_mask, bool build_image);
 int launch_backward_dw_tc(const EncodeArgs &a, const float *dx, const unsigned *dx_absmax, float *dW, cudaStream_t st);
 
 struct BackwardArgs {
@@ -514,8 +514,11 @@ size_t encode_backward_workspace_bytes(const c2v_dims *d, int B, int L)
 
 int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeArgs &a_in, int B,
                            const float *cv, const float *attention, const float *d_cv, const float *d_att,
-                           const c2v_grads *g, void *ws, size_t ws_bytes, cudaStream_t st, const float *x_stash)
+                           const c2v_grads *g, void *ws, size_t ws_bytes, cudaStream_t st, const float *x_stash, int phase)
 {
+    // phase 0: the whole backward.  Phases 1 / 2 split it where the path table's gradient is complete (all state between
+    // the two calls lives in the workspace): 1 = per-row work + dC of the path sub-vector, 2 = dC of start / end + dW.
+    // Only the tensor-core path with a stashed x splits; every other path does everything in phase 1.
     EncodeArgs a = a_in;
     if (a.H > 32 * MAXC) {
         set_error("encode backward supports encode_size <= %d (got %d)", 32 * MAXC, a.H);
@@ -533,6 +536,20 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     float *w_t = reinterpret_cast<float *>(base + o); o += align_up((size_t)a.D * Hs * 4, 1024);
     unsigned *dx_absmax = reinterpret_cast<unsigned *>(base + o); o += 1024;
     void *dc_ws = base + o;
+    {
+        const char *dc_env0 = getenv("C2V_BACKWARD_DC"), *dw_env0 = getenv("C2V_BACKWARD_DW");
+        const bool split_ok = x_stash && (a.H & 3) == 0 && backward_dc_tc_ok(a) && backward_dw_tc_ok(a) &&
+                              !(dc_env0 && !strcmp(dc_env0, "ffma")) && !(dw_env0 && !strcmp(dw_env0, "ffma"));
+        if (phase == 2) {
+            if (!split_ok) return C2V_OK;                       // phase 1 already did everything
+            a.n_tiles = (int)((a.N + TM - 1) / TM);
+            int rc2 = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st,
+                                            5, false);
+            if (rc2 != C2V_OK) return rc2;
+            return launch_backward_dw_tc(a, dx, dx_absmax, g->input_linear, st);
+        }
+        if (phase == 1 && !split_ok) phase = 0;
+    }
     C2V_CUDA_OK(cudaMemsetAsync(dx_absmax, 0, 4, st));
     memset(&a.ws, 0, sizeof(a.ws));
     a.ws.w_t = w_t;
@@ -574,7 +591,9 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
         if (a.H <= 128) backward_rows_lite_kernel<1><<<sms * 16, 256, 0, st>>>(a, b);
         else backward_rows_lite_kernel<2><<<sms * 8, 256, 0, st>>>(a, b);
         C2V_LAUNCH_OK("backward_rows_lite_kernel");
-        rc = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st);
+        if (phase == 1)                                         // path sub-vector only; start / end + dW follow in phase 2
+            return launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st, 2, true);
+        rc = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st, 7, true);
         if (rc != C2V_OK) return rc;
         const char *dw_env2 = getenv("C2V_BACKWARD_DW");
         if (backward_dw_tc_ok(a) && !(dw_env2 && !strcmp(dw_env2, "ffma")))
@@ -592,7 +611,7 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
     kern<<<grid, THREADS, smem, st>>>(a, b, Hs);
     C2V_LAUNCH_OK("backward_rows_kernel");
     if (dc_tc) {
-        rc = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st);
+        rc = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st, 7, true);
         if (rc != C2V_OK) return rc;
     }
 

@@ -80,8 +80,13 @@ split_wt_kernel(const float *__restrict__ W, int H, int E, const unsigned *__res
 __global__ void __launch_bounds__(dct::THREADS, 1)
 backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const unsigned *__restrict__ dx_absmax,
                       const uint8_t *__restrict__ wt_img, const float *__restrict__ wt_hdr,
-                      float *__restrict__ g_emb_t, float *__restrict__ g_emb_p)
+                      float *__restrict__ g_emb_t, float *__restrict__ g_emb_p, const int sv_mask)
 {
+    // sv_mask: which sub-vectors (bit 0 start, 1 path, 2 end) this launch handles.  The training step runs the path
+    // sub-vector first (mask 2): the path table's gradient is then complete and its data-parallel reduction can overlap
+    // the start / end launch (mask 5) -- see ShardedFlatAdam.early_step.
+    const int last_sv = (sv_mask & 4) ? 2 : ((sv_mask & 2) ? 1 : 0);
+    const int n_sv = ((sv_mask >> 0) & 1) + ((sv_mask >> 1) & 1) + ((sv_mask >> 2) & 1);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -174,14 +179,15 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
     } else if (warp == dct::W_WARP) {
         // =============================== W^T PRODUCER ===============================
         if (lane == 0) {
-            const int n_items = my_tiles * dct::NB;
+            const int n_items = my_tiles * 2 * n_sv;
             int kb6 = 0;
+            while (!((sv_mask >> (kb6 >> 1)) & 1)) kb6 += 2;                 // first active sub-vector
             for (int it = 0; it < n_items; ++it) {
                 const int bs = it & 1;
                 mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(it >> 1)) & 1u) ^ 1u, status);
                 mbar_arrive_expect_tx(bar_bfull + 8 * bs, dct::B_SLOT);
                 bulk_copy_g2s(base + dct::SMEM_B_OFF + bs * dct::B_SLOT, wt_img + (size_t)kb6 * dct::B_SLOT, dct::B_SLOT, bar_bfull + 8 * bs);
-                if (++kb6 == dct::NB) kb6 = 0;
+                do { if (++kb6 == dct::NB) kb6 = 0; } while (!((sv_mask >> (kb6 >> 1)) & 1));
             }
         }
         __syncwarp();
@@ -193,6 +199,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
             mbar_wait(bar_afull + 8 * as, ((uint32_t)(tl >> 1)) & 1u, status);
 #pragma unroll 1
             for (int sv = 0; sv < 3; ++sv) {
+                if (!((sv_mask >> sv) & 1)) continue;
                 mbar_wait(bar_tempty + 8 * sv, ((uint32_t)tl & 1u) ^ 1u, status);      // scatter of the previous tile drained
 #pragma unroll 1
                 for (int kb = 0; kb < 2; ++kb, ++it) {
@@ -215,7 +222,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                         umma_commit(bar_bempty + 8 * bs);
                         if (kb == 1) {
                             umma_commit(bar_tfull + 8 * sv);
-                            if (sv == 2) umma_commit(bar_aempty + 8 * as);
+                            if (sv == last_sv) umma_commit(bar_aempty + 8 * as);
                         }
                     }
                     __syncwarp();
@@ -235,6 +242,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
             if (ie < 0 || ie >= a.T) ie = 0;
 #pragma unroll 1
             for (int sv = 0; sv < 3; ++sv) {
+                if (!((sv_mask >> sv) & 1)) continue;
                 float *dst = sv == 1 ? g_emb_p + (size_t)ip * a.Et : g_emb_t + (size_t)(sv == 0 ? is : ie) * a.Et;
                 mbar_wait(bar_tfull + 8 * sv, (uint32_t)tl & 1u, status);
                 tc_fence_after();
@@ -275,25 +283,28 @@ size_t backward_dc_tc_workspace_bytes() { return 1024 + dct::IMG_BYTES; }
 
 // ws: [0, 1024) header {1/scale, scale} | W^T image
 int launch_backward_dc_tc(const EncodeArgs &a_in, const float *W, const float *dx, const unsigned *dx_absmax, void *ws,
-                          float *g_emb_t, float *g_emb_p, cudaStream_t st)
+                          float *g_emb_t, float *g_emb_p, cudaStream_t st, int sv_mask, bool build_image)
 {
     EncodeArgs a = a_in;
     a.n_tiles = (int)((a.N + dct::ROWS - 1) / dct::ROWS);
     float *hdr = static_cast<float *>(ws);
     uint8_t *img = static_cast<uint8_t *>(ws) + 1024;
     unsigned *mxbits = reinterpret_cast<unsigned *>(static_cast<uint8_t *>(ws) + 512);
-    C2V_CUDA_OK(cudaMemsetAsync(mxbits, 0, 4, st));
-    wt_absmax_kernel<<<48, 256, 0, st>>>(W, a.H * a.D, mxbits);
-    C2V_LAUNCH_OK("wt_absmax_kernel");
-    split_wt_kernel<<<48, 256, 0, st>>>(W, a.H, a.Et, mxbits, img, hdr);
-    C2V_LAUNCH_OK("split_wt_kernel");
+    if (build_image) {
+        C2V_CUDA_OK(cudaMemsetAsync(mxbits, 0, 4, st));
+        wt_absmax_kernel<<<48, 256, 0, st>>>(W, a.H * a.D, mxbits);
+        C2V_LAUNCH_OK("wt_absmax_kernel");
+        split_wt_kernel<<<48, 256, 0, st>>>(W, a.H, a.Et, mxbits, img, hdr);
+        C2V_LAUNCH_OK("split_wt_kernel");
+    }
+    if ((sv_mask & 7) == 0) return C2V_OK;
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     C2V_CUDA_OK(cudaFuncSetAttribute(backward_dc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dct::SMEM_BYTES));
     int grid = a.n_tiles < sms ? a.n_tiles : sms;
     if (grid < 1) grid = 1;
-    backward_dc_tc_kernel<<<grid, dct::THREADS, dct::SMEM_BYTES, st>>>(a, dx, dx_absmax, img, hdr, g_emb_t, g_emb_p);
+    backward_dc_tc_kernel<<<grid, dct::THREADS, dct::SMEM_BYTES, st>>>(a, dx, dx_absmax, img, hdr, g_emb_t, g_emb_p, sv_mask & 7);
     C2V_LAUNCH_OK("backward_dc_tc_kernel");
     return C2V_OK;
 }

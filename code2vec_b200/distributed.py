@@ -121,24 +121,32 @@ class ShardedFlatAdam:
     torch.optim.Adam (main.py:138) -- every rank ends a step with bit-identical parameters.
 
     Layout: parameters live in ONE flat fp32 buffer (views, like FlatAdam), gradients in TWO flat buckets that alternate
-    between steps (`.grad` of every parameter is re-pointed after each step); the flat length is padded to a multiple of
-    4 * world and rank r owns slice r (exp_avg / exp_avg_sq exist only for the owned slice: 1/world of the state).
+    between steps (`.grad` of every parameter is re-pointed after each step).  The flat buffers consist of one or two
+    REGIONS, each padded to a multiple of 4 * world; rank r owns slice r of every region (exp_avg / exp_avg_sq exist only
+    for the owned slices: 1/world of the state).  With `early=[p, ...]` those parameters form region 0: their gradients
+    are complete before the backward ends (path_embedding, once the path sub-vector of dC has run), and `early_step()` --
+    called from inside the backward -- reduces / updates / broadcasts region 0 on a side stream while the rest of the
+    backward is still computing; `step()` then handles region 1 and joins.
 
     transport
       "nvls"  buffers are symmetric memory (torch.distributed._symmetric_memory: plumbing only -- allocation, the
-              multicast mapping, the cross-GPU barriers); one `c2v_adam_step_sharded` launch per rank reduces the slice's
-              gradients in the NVSwitch (`multimem.ld_reduce`), runs Adam, and multicasts the new parameters
+              multicast mapping, the cross-GPU barriers); one `c2v_adam_step_sharded` launch per rank and region reduces
+              the slice's gradients in the NVSwitch (`multimem.ld_reduce`), runs Adam, and multicasts the new parameters
               (`multimem.st`), zero-filling the other bucket meanwhile.  No NCCL call in the step.
       "p2p"   same kernel, peer pointers instead of the multicast mapping (NVLink loads / stores, rank-ordered sum).
       "nccl"  reduce_scatter -> `c2v_adam_step` on the slice -> all_gather (two NCCL collectives; the fallback when
               symmetric memory is unavailable, and what the gloo CPU tests drive with a stand-in kernel).
-      "auto"  nvls if the group has multicast support, else p2p if symmetric memory works, else nccl.
+      "auto"  nvls or p2p, whichever is faster on this group (timed at construction), else nccl.
     """
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None, transport="auto"):
-        self.params = [p for p in params if p.requires_grad]
-        if not self.params:
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, group=None, transport="auto",
+                 early=()):
+        params = [p for p in params if p.requires_grad]
+        if not params:
             raise ValueError("no trainable parameters")
+        early_ids = {id(p) for p in early}
+        first = [p for p in params if id(p) in early_ids]
+        self.params = first + [p for p in params if id(p) not in early_ids]      # flat order: early region first
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
@@ -148,26 +156,43 @@ class ShardedFlatAdam:
             raise TypeError("parameters must be fp32")
         self.numel = sum(p.numel() for p in self.params)
         q = 4 * self.world
-        self.padded = (self.numel + q - 1) // q * q
-        self.slice_n = self.padded // self.world
-        self.slice_begin = self.rank * self.slice_n
+        pad = lambda n: (n + q - 1) // q * q
+        n_early = sum(p.numel() for p in first)
+        # regions: (begin, length) in the flat buffers; region 0 = the early parameters (absent when there are none)
+        self.regions = ([(0, pad(n_early))] if n_early else []) + \
+            [(pad(n_early) if n_early else 0, pad(self.numel - n_early))]
+        self.padded = sum(n for _, n in self.regions)
+        # this rank's slice of every region, and where its optimizer state sits in exp_avg / exp_avg_sq
+        self.slices, o = [], 0
+        for begin, n in self.regions:
+            sl = n // self.world
+            self.slices.append((begin + self.rank * sl, sl, o))
+            o += sl
+        self.state_numel = o
         self._auto = transport == "auto"
         self.transport, self._hdl = self._allocate(transport, dev)
-        o = 0
         self._grad_views = ([], [])
-        for p in self.params:
+        self.flat_param.zero_()
+        pos = {}
+        o = 0
+        for i, p in enumerate(self.params):
             if p.device != dev or p.dtype != dt:
                 raise ValueError("parameters must share device and dtype")
-            n = p.numel()
+            if n_early and i == len(first):
+                o = self.regions[1][0]                           # region 1 starts after region 0's padding
+            pos[i] = o
+            o += p.numel()
+        for i, p in enumerate(self.params):
+            n, o = p.numel(), pos[i]
             self.flat_param[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[o:o + n].view_as(p)
             for k in (0, 1):
                 self._grad_views[k].append(self.buckets[k][o:o + n].view_as(p))
-            o += n
-        self.flat_param[self.numel:].zero_()
-        self.exp_avg = torch.zeros(self.slice_n, dtype=dt, device=dev)
-        self.exp_avg_sq = torch.zeros(self.slice_n, dtype=dt, device=dev)
+        self.exp_avg = torch.zeros(self.state_numel, dtype=dt, device=dev)
+        self.exp_avg_sq = torch.zeros(self.state_numel, dtype=dt, device=dev)
         self.t, self.cur = 0, 0
+        self._early_done = False
+        self._side = torch.cuda.Stream(dev) if (dev.type == "cuda" and len(self.regions) > 1) else None
         self._point_grads(0)
         if self.world > 1:
             dist.barrier(group)
@@ -178,7 +203,7 @@ class ShardedFlatAdam:
     def _calibrate(self):
         """transport="auto" with a multicast mapping available: time the fused kernel both ways on the real buffers
         (zero gradients, zero optimizer state, lr = 0: nothing changes) and keep the faster -- at 2 GPUs peer loads/stores
-        beat the in-switch reduction (0.60 vs 0.95 ms for 364.6 MB), at 8 the multicast halves the bytes per link."""
+        beat the in-switch reduction (0.57 vs 0.93 ms for 364.6 MB), at 8 the multicast wins (0.82 vs 1.00 ms)."""
         dev = self.flat_param.device
         res = {}
         saved = (self.lr, self.weight_decay)
@@ -241,21 +266,22 @@ class ShardedFlatAdam:
         return self.buckets[self.cur]
 
     def state_bytes(self):
-        return 4 * (2 * self.slice_n)
+        return 4 * (2 * self.state_numel)
 
     def zero_grad(self):
         self.buckets[self.cur].zero_()
 
     # ---- the step -----------------------------------------------------------------------------------------------------
-    def _adam_slice(self, p_slice, g_slice, zero_grad=False):
-        """c2v_adam_step on the owned slice (the gloo CPU tests replace this method with a torch stand-in)"""
+    def _adam_slice(self, p_slice, g_slice, zero_grad=False, state=None):
+        """c2v_adam_step on an owned slice (the gloo CPU tests replace this method with a torch stand-in)"""
         import ctypes
         from . import _lib
         lib = _lib.load()
         P = lambda t: ctypes.c_void_p(t.data_ptr())
+        m, v = state if state is not None else (self.exp_avg, self.exp_avg_sq)
         dev = p_slice.device
         with torch.cuda.device(dev):
-            rc = lib.c2v_adam_step(P(p_slice), P(g_slice), P(self.exp_avg), P(self.exp_avg_sq), p_slice.numel(), self.lr,
+            rc = lib.c2v_adam_step(P(p_slice), P(g_slice), P(m), P(v), p_slice.numel(), self.lr,
                                    self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, 1.0 / self.world,
                                    1 if zero_grad else 0, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc, "c2v_adam_step")
@@ -266,45 +292,72 @@ class ShardedFlatAdam:
         except (RuntimeError, NotImplementedError):          # gloo (CPU tests) has no reduce_scatter
             tmp = full.clone()
             dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
-            out.copy_(tmp[self.slice_begin:self.slice_begin + self.slice_n])
+            sl = full.numel() // self.world
+            out.copy_(tmp[self.rank * sl:(self.rank + 1) * sl])
+
+    def _fused_region(self, r, cur, nxt):
+        """barrier -> c2v_adam_step_sharded on this rank's slice of region r -> barrier, on the current stream"""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        hp, hg = self._hdl[0], self._hdl[1 + cur]
+        dev = self.flat_param.device
+        V = ctypes.c_void_p
+        use_mc = self.transport == "nvls"
+        pp = (V * self.world)(*[int(x) for x in hp.buffer_ptrs])
+        gp = (V * self.world)(*[int(x) for x in hg.buffer_ptrs])
+        lo, n, so = self.slices[r]
+        rb, rn = self.regions[r]
+        with torch.cuda.device(dev):
+            hg.barrier(channel=2 * r)                        # every rank's backward has finished writing this region
+            rc = lib.c2v_adam_step_sharded(
+                V(self.flat_param.data_ptr()), V(int(hp.multicast_ptr)) if use_mc else None,
+                V(int(hg.multicast_ptr)) if use_mc else None, pp, gp, self.world, V(self.exp_avg.data_ptr() + 4 * so),
+                V(self.exp_avg_sq.data_ptr() + 4 * so), lo, n, V(self.buckets[nxt].data_ptr() + 4 * rb), rn, self.lr,
+                self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, 1.0 / self.world,
+                V(torch.cuda.current_stream(dev).cuda_stream))
+            _lib.check(rc, "c2v_adam_step_sharded")
+            hp.barrier(channel=2 * r + 1)                    # every rank's parameter stores of this region have landed here
+
+    def early_step(self):
+        """Called from inside the backward once the early parameters' gradients are complete (Code2Vec.on_path_grads_ready):
+        reduce + Adam + broadcast of region 0 on a side stream, overlapping the rest of the backward."""
+        if self.world == 1 or self.transport == "nccl" or len(self.regions) < 2 or self._early_done:
+            return
+        dev = self.flat_param.device
+        self.t += 1
+        self._side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._side):
+            self._fused_region(0, self.cur, 1 - self.cur)
+        self._early_done = True
 
     def step(self):
         """reduce this step's gradients over the ranks (mean), Adam, parameters identical everywhere afterwards; the
         other bucket is left zeroed and becomes the target of the next backward (main.py:171 + :175)."""
-        import ctypes
-        self.t += 1
         cur, nxt = self.cur, 1 - self.cur
-        lo, hi = self.slice_begin, self.slice_begin + self.slice_n
+        if not self._early_done:
+            self.t += 1
         if self.world == 1:                                      # one launch, gradient zeroed in the same pass, no swap
             self._adam_slice(self.flat_param, self.buckets[cur], zero_grad=True)
             for p in self.params:
                 torch.autograd.graph.increment_version(p)
             return
         if self.transport == "nccl":
-            g_slice = torch.empty(self.slice_n, dtype=torch.float32, device=self.flat_param.device)
-            self._reduce_scatter(g_slice, self.buckets[cur])
-            self._adam_slice(self.flat_param[lo:hi], g_slice)
-            dist.all_gather_into_tensor(self.flat_param, self.flat_param[lo:hi].clone(), group=self.group)
+            dev = self.flat_param.device
+            for r, (rb, rn) in enumerate(self.regions):
+                lo, n, so = self.slices[r]
+                g_slice = torch.empty(n, dtype=torch.float32, device=dev)
+                self._reduce_scatter(g_slice, self.buckets[cur][rb:rb + rn])
+                self._adam_slice(self.flat_param[lo:lo + n], g_slice, state=(self.exp_avg[so:so + n], self.exp_avg_sq[so:so + n]))
+                dist.all_gather_into_tensor(self.flat_param[rb:rb + rn], self.flat_param[lo:lo + n].clone(), group=self.group)
             self.buckets[nxt].zero_()
         else:
-            from . import _lib
-            lib = _lib.load()
-            hp, hg = self._hdl[0], self._hdl[1 + cur]
-            dev = self.flat_param.device
-            V = ctypes.c_void_p
-            use_mc = self.transport == "nvls"
-            pp = (V * self.world)(*[int(x) for x in hp.buffer_ptrs])
-            gp = (V * self.world)(*[int(x) for x in hg.buffer_ptrs])
-            with torch.cuda.device(dev):
-                hg.barrier(channel=0)                            # every rank's backward has finished writing its bucket
-                rc = lib.c2v_adam_step_sharded(
-                    V(self.flat_param.data_ptr()), V(int(hp.multicast_ptr)) if use_mc else None,
-                    V(int(hg.multicast_ptr)) if use_mc else None, pp, gp, self.world, V(self.exp_avg.data_ptr()),
-                    V(self.exp_avg_sq.data_ptr()), lo, self.slice_n, V(self.buckets[nxt].data_ptr()), self.padded, self.lr,
-                    self.betas[0], self.betas[1], self.eps, self.weight_decay, self.t, 1.0 / self.world,
-                    V(torch.cuda.current_stream(dev).cuda_stream))
-                _lib.check(rc, "c2v_adam_step_sharded")
-                hp.barrier(channel=1)                            # every rank's parameter stores have landed here
+            first = 1 if self._early_done else 0
+            for r in range(first, len(self.regions)):
+                self._fused_region(r, cur, nxt)
+            if self._early_done:
+                torch.cuda.current_stream(self.flat_param.device).wait_stream(self._side)
+        self._early_done = False
         self._point_grads(nxt)
         for p in self.params:                                    # raw-pointer writes: bump the version counters
             torch.autograd.graph.increment_version(p)
@@ -314,6 +367,9 @@ def ddp_step(model, optimizer, bucket, starts, paths, ends, label, loss_fn):
     """One training step of main.py:171-175 on this rank's shard of the global batch."""
     if isinstance(optimizer, (ShardedFlatAdam, FlatAdam)) and hasattr(model, "fuse_grad_accumulation"):
         model.fuse_grad_accumulation = True                  # .grad are persistent views into a flat bucket: accumulate in place
+        if isinstance(optimizer, ShardedFlatAdam) and len(optimizer.regions) > 1 and optimizer.world > 1 and \
+                optimizer.transport != "nccl":
+            model.on_path_grads_ready = optimizer.early_step # region 0 is reduced while the backward is still running
     if isinstance(optimizer, ShardedFlatAdam):               # reduction + optimizer + broadcast are one kernel per rank
         if loss_fn is None:                                  # fused loss: the [b, C] logits are never written
             loss = model.forward_loss(starts, paths, ends, label)[0]

@@ -351,7 +351,7 @@ def label_backward(dims, params, cv, d_out, need_cv=True, need_w=True, need_b=Tr
 
 
 def encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p=0.0, training=False,
-                    seed=0, grads_out=None, x_stash=None):
+                    seed=0, grads_out=None, x_stash=None, between_phases=None):
     """Gradients of the six encode parameters; returns dict name -> tensor.  x_stash: what encode_forward(stash=True)
     returned for this batch (skips the re-gather + recompute GEMM)."""
     lib = _lib.load()
@@ -368,9 +368,14 @@ def encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, sha
         cv = _f32c(cv, "code_vector"); att = _f32c(att, "attention")
         d_cv = _f32c(d_cv, "d_code_vector")
         d_att = _f32c(d_att, "d_attention") if d_att is not None else None
-        rc = lib.c2v_encode_backward_stashed(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
-                                             B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(x_stash),
-                                             _ptr(d_cv), _ptr(d_att), ctypes.byref(grads),
-                                             _ptr(ws), nbytes, _stream(dev))
-        _lib.check(rc, "c2v_encode_backward")
+        # between_phases: called after the path sub-vector's gradients are complete (c2v_encode_backward_phased), e.g. to
+        # start their data-parallel reduction on another stream while start / end / dW are still being computed
+        for phase in ((1, 2) if between_phases is not None else (0,)):
+            rc = lib.c2v_encode_backward_phased(ctypes.byref(dims), ctypes.byref(params), _ptr(starts), _ptr(paths), _ptr(ends),
+                                                B, L, ctypes.byref(drop), _ptr(cv), _ptr(att), _ptr(x_stash),
+                                                _ptr(d_cv), _ptr(d_att), ctypes.byref(grads),
+                                                _ptr(ws), nbytes, phase, _stream(dev))
+            _lib.check(rc, "c2v_encode_backward")
+            if phase == 1:
+                between_phases()
     return g

@@ -72,8 +72,9 @@ class _EncodeFn(torch.autograd.Function):
             grads_out = {k: t.grad for k, t in big}
             for k in ("ln_weight", "ln_bias", "attention"):
                 grads_out[k] = torch.empty(shapes[k], dtype=torch.float32, device=cv.device)   # overwritten by the kernels
+        hook = getattr(ctx.cache, "on_path_grads_ready", None) if fuse else None
         g = CF.encode_backward(dims, params, starts, paths, ends, cv, att, d_cv, d_att, shapes, drop_p, training, seed,
-                               grads_out=grads_out, x_stash=ctx.x_stash)
+                               grads_out=grads_out, x_stash=ctx.x_stash, between_phases=hook)
         ctx.x_stash = None
         if fuse:
             return (None, None, None, g["ln_weight"], g["ln_bias"], g["attention"], None, None, None, None, None, None,
@@ -191,6 +192,9 @@ class Code2Vec(nn.Module):
         # True: the backward adds the table / input_linear gradients directly into the parameters' existing .grad buffers
         # (see _EncodeFn.backward); needs dense fp32 .grad tensors to exist before the backward, e.g. a flat gradient bucket
         self.fuse_grad_accumulation = False
+        # callable run by the backward once path_embedding's gradient is complete (fused accumulation only): the sharded
+        # optimizer starts that table's data-parallel reduction there (ShardedFlatAdam.early_step)
+        self.on_path_grads_ready = None
         self._lab_cache = CF.PrepCache()
 
     # -- helpers ---------------------------------------------------------------------------
@@ -214,6 +218,7 @@ class Code2Vec(nn.Module):
     def forward(self, starts, paths, ends, label):
         self._enc_cache.raise_deferred()
         self._enc_cache.fuse_grad_accumulation = self.fuse_grad_accumulation
+        self._enc_cache.on_path_grads_ready = self.on_path_grads_ready
         option = self.option
         dims = self._dims()
         training = self.training and self.input_dropout is not None
@@ -249,6 +254,7 @@ class Code2Vec(nn.Module):
             raise NotImplementedError("forward_loss() needs the plain label head")
         self._enc_cache.raise_deferred()
         self._enc_cache.fuse_grad_accumulation = self.fuse_grad_accumulation
+        self._enc_cache.on_path_grads_ready = self.on_path_grads_ready
         dims = self._dims()
         training = self.training and self.input_dropout is not None
         drop_p = float(self.option.dropout_prob) if training else 0.0

@@ -12,18 +12,20 @@ torch.cuda.set_device(local); dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
 shapes = [(1000, 37), (513,), (64, 129), (7,), (300, 128)]
-for transport in ("nvls", "p2p", "nccl"):
+for transport, use_early in (("nvls", False), ("p2p", False), ("nccl", False), ("nvls", True), ("p2p", True)):
     try:
         g = torch.Generator(device=dev).manual_seed(5)
         params = [torch.nn.Parameter(torch.randn(*s, generator=g, device=dev)) for s in shapes]
         ref = [torch.nn.Parameter(p.detach().clone()) for p in params]
         ropt = torch.optim.Adam(ref, lr=0.01, weight_decay=0.01)
-        opt = ShardedFlatAdam(params, lr=0.01, weight_decay=0.01, transport=transport)
+        opt = ShardedFlatAdam(params, lr=0.01, weight_decay=0.01, transport=transport, early=[params[2]] if use_early else ())
         for step in range(4):
             gr = torch.Generator(device=dev).manual_seed(100 * step + rank)
             mine = [torch.randn(*s, generator=gr, device=dev) for s in shapes]
             for p, m in zip(params, mine):
                 p.grad.add_(m)                       # backward accumulates into the (zeroed) bucket views
+            if use_early:
+                opt.early_step()                     # region 0 (params[2]) on the side stream, as from inside the backward
             opt.step()
             allg = []
             for r in range(world):
@@ -37,7 +39,7 @@ for transport in ("nvls", "p2p", "nccl"):
         flat = opt.flat_param.clone()
         ref0 = flat.clone(); dist.broadcast(ref0, 0)
         same = bool(torch.equal(flat, ref0))
-        print(f"[rank {rank}] {transport}: transport={opt.transport} max|p - torch.Adam| = {err:.2e} replicas identical: {same}", flush=True)
+        print(f"[rank {rank}] {transport}{' + early region' if use_early else ''}: transport={opt.transport} max|p - torch.Adam| = {err:.2e} replicas identical: {same}", flush=True)
         ok &= err < 2e-6 and same
         del opt
     except Exception as ex:

@@ -277,12 +277,25 @@ def test_fused_grad_accumulation_equals_autograd_accumulation(name):
             prm.grad = torch.randn_like(prm) * 0.01
         before = {k: v.grad.clone() for k, v in m.named_parameters()}
         m.fuse_grad_accumulation = fuse
+        calls = []
+        if fuse:                                         # the two-phase backward: hook runs once path_embedding.grad is complete
+            path_before = m.path_embedding.weight.grad.clone()
+            def hook():
+                torch.cuda.synchronize()
+                calls.append((m.path_embedding.weight.grad - path_before).cpu().numpy())
+            m.on_path_grads_ready = hook
         ptrs = {k: v.grad.data_ptr() for k, v in m.named_parameters()}
         out, cv, att = m.forward(s, p, e, lab)
         F.nll_loss(F.log_softmax(out, dim=1), lab).backward()
         for k, v in m.named_parameters():
             assert v.grad.data_ptr() == ptrs[k], k       # .grad buffers stay where they are (flat-bucket views survive)
         res.append({k: (v.grad - before[k]).cpu().numpy() for k, v in m.named_parameters()})
+        if fuse:
+            assert len(calls) == 1
+            ref = rec["grads"]["path_embedding.weight"]      # already complete when the hook ran, untouched afterwards
+            assert np.abs(calls[0] - ref).max() <= _tol(ref) + 2e-8
+            assert np.array_equal(calls[0], res[-1]["path_embedding.weight"]) or \
+                np.abs(calls[0] - res[-1]["path_embedding.weight"]).max() <= 1e-9
     for k in res[0]:
         ref = rec["grads"][k]
         assert np.abs(res[1][k] - ref).max() <= _tol(ref) + 2e-8, k          # fused path vs the reference's autograd
