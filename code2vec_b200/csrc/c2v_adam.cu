@@ -67,8 +67,10 @@ __device__ __forceinline__ void mm_st(float *mc, float4 v) {
                  ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// 128-thread CTAs (<= 64 registers): 8 K registers per CTA, so that the kernel can share SMs with the persistent tensor-core
+// backward kernels (22 warps x 72-80 registers leave ~9-15 K of the 64 K registers) when it runs on a side stream.
 template <bool MULTIMEM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 adam_step_sharded_kernel(const float *__restrict__ p_local, float *__restrict__ p_mc, const float *__restrict__ g_mc,
                          const AdamPeers peers, int world, float4 *__restrict__ m, float4 *__restrict__ v,
                          long long slice_begin, long long slice_n4, float4 *__restrict__ zero_buf, long long zero_n4,
@@ -204,18 +206,18 @@ extern "C" int c2v_adam_step_sharded(const float *param_local, float *param_mult
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long n4 = slice_n / 4, z4 = zero_buffer ? zero_n / 4 : 0;
-    long long blocks = ((n4 > z4 ? n4 : z4) + 255) / 256;
-    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    long long blocks = ((n4 > z4 ? n4 : z4) + 127) / 128;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
     if (blocks < 4) blocks = 4;
     blocks = blocks / 4 * 4;                                  // every 4th CTA zero-fills
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (mm)
-        adam_step_sharded_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(
+        adam_step_sharded_kernel<true><<<(unsigned)blocks, 128, 0, st>>>(
             param_local, param_multicast, grad_multicast, peers, world, reinterpret_cast<float4 *>(exp_avg_slice),
             reinterpret_cast<float4 *>(exp_avg_sq_slice), slice_begin, n4, reinterpret_cast<float4 *>(zero_buffer), z4,
             step_size, 1.0f - beta1, beta2, 1.0f - beta2, inv_sqrt_bc2, eps, weight_decay, grad_scale);
     else
-        adam_step_sharded_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(
+        adam_step_sharded_kernel<false><<<(unsigned)blocks, 128, 0, st>>>(
             param_local, param_multicast, grad_multicast, peers, world, reinterpret_cast<float4 *>(exp_avg_slice),
             reinterpret_cast<float4 *>(exp_avg_sq_slice), slice_begin, n4, reinterpret_cast<float4 *>(zero_buffer), z4,
             step_size, 1.0f - beta1, beta2, 1.0f - beta2, inv_sqrt_bc2, eps, weight_decay, grad_scale);
