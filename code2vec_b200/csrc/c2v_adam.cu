@@ -131,6 +131,108 @@ adam_step_sharded_kernel(const float *__restrict__ p_local, float *__restrict__ 
     __threadfence_system();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same step driven by bulk-async copies (TMA) instead of thousands of threads: one warp per CTA, 28 KB of shared
+// memory.  Purpose: run on a side stream NEXT TO the persistent tensor-core backward kernels, which own every SM
+// (22 warps x 72-80 registers, 197 KB of shared memory) and leave room for exactly this much -- the thread-per-element
+// kernel above cannot get enough CTAs resident beside them to keep NVLink busy.  Per chunk: lane 0 issues one
+// cp.async.bulk per rank (peer gradient slice -> shared memory, completion on an mbarrier; 2 stages = the bytes in flight),
+// the warp sums the `world` copies in rank order, runs Adam on the chunk (p, m, v are local: plain vector loads / stores),
+// writes the new parameters into the stage's first buffer and lane 0 issues one bulk store per rank (shared -> peer
+// parameter buffer).  Peer pointers only (no multicast): region 0 of ShardedFlatAdam (early_step).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int AB_STAGES = 2, AB_STAGE_BYTES = 14 * 1024;
+
+__device__ __forceinline__ uint32_t ab_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(32)
+adam_step_bulk_kernel(const float *__restrict__ p_local, const AdamPeers peers, int world, float *__restrict__ m,
+                      float *__restrict__ v, long long slice_begin, long long slice_n, int chunk,
+                      float step_size, float one_minus_b1, float b2, float one_minus_b2, float inv_sqrt_bc2, float eps,
+                      float wd, float gscale)
+{
+    extern __shared__ __align__(128) unsigned char ab_raw[];
+    __shared__ __align__(8) unsigned long long ab_bar[AB_STAGES];
+    const int lane = threadIdx.x;
+    const long long n_chunks = (slice_n + chunk - 1) / chunk;
+    const long long my_chunks = (n_chunks - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x;
+    if (lane == 0) {
+        for (int s = 0; s < AB_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ab_smem(&ab_bar[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](long long k) {                               // lane 0: loads of this CTA's k-th chunk into stage k & 1
+        const long long c = (long long)blockIdx.x + k * gridDim.x;
+        const long long off = c * chunk;
+        const int len = (int)((slice_n - off) < chunk ? (slice_n - off) : chunk);
+        const uint32_t bytes = (uint32_t)len * 4u;
+        const int st = (int)(k & 1);
+        const uint32_t bar = ab_smem(&ab_bar[st]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * (uint32_t)world) : "memory");
+        for (int r = 0; r < world; ++r) {
+            const uint32_t dst = ab_smem(ab_raw + (size_t)st * AB_STAGE_BYTES + (size_t)r * chunk * 4);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(peers.grad[r] + slice_begin + off), "r"(bytes), "r"(bar) : "memory");
+        }
+    };
+    auto upd = [&](float &pp, float gg, float &mm, float &vv) {
+        float gr = gg * gscale;
+        if (wd != 0.0f) gr = fmaf(wd, pp, gr);
+        mm = mm + (gr - mm) * one_minus_b1;
+        vv = vv * b2 + one_minus_b2 * gr * gr;
+        const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+        pp = pp - step_size * (mm / denom);
+    };
+    if (lane == 0 && my_chunks > 0) issue(0);
+    for (long long k = 0; k < my_chunks; ++k) {
+        const int st = (int)(k & 1);
+        if (lane == 0 && k + 1 < my_chunks) {
+            // the other stage's buffers were the source of chunk k-1's bulk stores: wait until those have READ them
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            issue(k + 1);
+        }
+        __syncwarp();
+        {   // wait for this stage's loads
+            const uint32_t bar = ab_smem(&ab_bar[st]), parity = (uint32_t)(k >> 1) & 1u;
+            uint32_t ok = 0;
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            }
+        }
+        const long long c = (long long)blockIdx.x + k * gridDim.x;
+        const long long off = c * chunk;
+        const int len = (int)((slice_n - off) < chunk ? (slice_n - off) : chunk);
+        float *stage = reinterpret_cast<float *>(ab_raw + (size_t)st * AB_STAGE_BYTES);
+        for (int i = lane * 4; i < len; i += 128) {               // len is a multiple of 4 (slices are)
+            float4 G = *reinterpret_cast<const float4 *>(stage + i);
+            for (int r = 1; r < world; ++r) {                      // rank order: replicas of the sum are bit-identical
+                const float4 x = *reinterpret_cast<const float4 *>(stage + (size_t)r * chunk + i);
+                G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
+            }
+            const long long e = off + i;                           // offset inside the slice
+            float4 P = *reinterpret_cast<const float4 *>(p_local + slice_begin + e);
+            float4 M = *reinterpret_cast<const float4 *>(m + e), V = *reinterpret_cast<const float4 *>(v + e);
+            upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+            *reinterpret_cast<float4 *>(m + e) = M; *reinterpret_cast<float4 *>(v + e) = V;
+            *reinterpret_cast<float4 *>(stage + i) = P;            // rank 0's buffer becomes the output staging
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the bulk stores
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t src = ab_smem(stage), bytes = (uint32_t)len * 4u;
+            for (int r = 0; r < world; ++r)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(peers.param[r] + slice_begin + off), "r"(src), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores performed before the kernel ends
+    __syncwarp();
+    __threadfence_system();
+}
+
 }  // namespace c2v
 
 using namespace c2v;
@@ -222,5 +324,45 @@ extern "C" int c2v_adam_step_sharded(const float *param_local, float *param_mult
             reinterpret_cast<float4 *>(exp_avg_sq_slice), slice_begin, n4, reinterpret_cast<float4 *>(zero_buffer), z4,
             step_size, 1.0f - beta1, beta2, 1.0f - beta2, inv_sqrt_bc2, eps, weight_decay, grad_scale);
     C2V_LAUNCH_OK("adam_step_sharded_kernel");
+    return C2V_OK;
+}
+
+extern "C" int c2v_adam_step_sharded_bulk(const float *param_local, float *const *param_peers, const float *const *grad_peers,
+                                          int32_t world, float *exp_avg_slice, float *exp_avg_sq_slice, int64_t slice_begin,
+                                          int64_t slice_n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                          int64_t step, float grad_scale, int32_t max_ctas, void *stream)
+{
+    if (!param_local || !param_peers || !grad_peers || !exp_avg_slice || !exp_avg_sq_slice || slice_n < 0 || slice_begin < 0 ||
+        step < 1 || world < 1 || world > 16 || ((slice_begin | slice_n) & 3)) {
+        set_error("c2v_adam_step_sharded_bulk: bad argument");
+        return C2V_EINVAL;
+    }
+    AdamPeers peers;
+    memset(&peers, 0, sizeof(peers));
+    uintptr_t align = reinterpret_cast<uintptr_t>(param_local) | reinterpret_cast<uintptr_t>(exp_avg_slice) |
+                      reinterpret_cast<uintptr_t>(exp_avg_sq_slice);
+    for (int r = 0; r < world; ++r) {
+        if (!param_peers[r] || !grad_peers[r]) { set_error("c2v_adam_step_sharded_bulk: NULL peer pointer %d", r); return C2V_EINVAL; }
+        peers.param[r] = param_peers[r]; peers.grad[r] = grad_peers[r];
+        align |= reinterpret_cast<uintptr_t>(param_peers[r]) | reinterpret_cast<uintptr_t>(grad_peers[r]);
+    }
+    if (align & 15) { set_error("c2v_adam_step_sharded_bulk: buffers must be 16-byte aligned"); return C2V_EINVAL; }
+    if (slice_n == 0) return C2V_OK;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    int dev = 0, sms = 0;
+    C2V_CUDA_OK(cudaGetDevice(&dev));
+    C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int chunk = AB_STAGE_BYTES / 4 / world / 4 * 4;          // floats per rank and stage (16-byte multiple)
+    const long long n_chunks = (slice_n + chunk - 1) / chunk;
+    long long grid = max_ctas > 0 ? max_ctas : sms;
+    if (grid > n_chunks) grid = n_chunks;
+    const int smem = AB_STAGES * AB_STAGE_BYTES;
+    C2V_CUDA_OK(cudaFuncSetAttribute(adam_step_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    adam_step_bulk_kernel<<<(unsigned)grid, 32, smem, static_cast<cudaStream_t>(stream)>>>(
+        param_local, peers, world, exp_avg_slice, exp_avg_sq_slice, slice_begin, slice_n, chunk, step_size, 1.0f - beta1, beta2,
+        1.0f - beta2, inv_sqrt_bc2, eps, weight_decay, grad_scale);
+    C2V_LAUNCH_OK("adam_step_bulk_kernel");
     return C2V_OK;
 }

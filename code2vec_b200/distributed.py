@@ -295,7 +295,28 @@ class ShardedFlatAdam:
             sl = full.numel() // self.world
             out.copy_(tmp[self.rank * sl:(self.rank + 1) * sl])
 
-    def _fused_region(self, r, cur, nxt):
+    def _bulk_region(self, r, cur):
+        """barrier -> c2v_adam_step_sharded_bulk (one warp + 28 KB of shared memory per CTA: fits beside the persistent
+        backward kernels) on this rank's slice of region r -> barrier, on the current (side) stream.  No zero-fill."""
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        hp, hg = self._hdl[0], self._hdl[1 + cur]
+        dev = self.flat_param.device
+        V = ctypes.c_void_p
+        pp = (V * self.world)(*[int(x) for x in hp.buffer_ptrs])
+        gp = (V * self.world)(*[int(x) for x in hg.buffer_ptrs])
+        lo, n, so = self.slices[r]
+        with torch.cuda.device(dev):
+            hg.barrier(channel=2 * r)
+            rc = lib.c2v_adam_step_sharded_bulk(
+                V(self.flat_param.data_ptr()), pp, gp, self.world, V(self.exp_avg.data_ptr() + 4 * so),
+                V(self.exp_avg_sq.data_ptr() + 4 * so), lo, n, self.lr, self.betas[0], self.betas[1], self.eps,
+                self.weight_decay, self.t, 1.0 / self.world, 0, V(torch.cuda.current_stream(dev).cuda_stream))
+            _lib.check(rc, "c2v_adam_step_sharded_bulk")
+            hp.barrier(channel=2 * r + 1)
+
+    def _fused_region(self, r, cur, nxt, zero_all=False):
         """barrier -> c2v_adam_step_sharded on this rank's slice of region r -> barrier, on the current stream"""
         import ctypes
         from . import _lib
@@ -307,7 +328,7 @@ class ShardedFlatAdam:
         pp = (V * self.world)(*[int(x) for x in hp.buffer_ptrs])
         gp = (V * self.world)(*[int(x) for x in hg.buffer_ptrs])
         lo, n, so = self.slices[r]
-        rb, rn = self.regions[r]
+        rb, rn = (0, self.padded) if zero_all else self.regions[r]     # which part of the OTHER bucket this launch zero-fills
         with torch.cuda.device(dev):
             hg.barrier(channel=2 * r)                        # every rank's backward has finished writing this region
             rc = lib.c2v_adam_step_sharded(
@@ -328,7 +349,7 @@ class ShardedFlatAdam:
         self.t += 1
         self._side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self._side):
-            self._fused_region(0, self.cur, 1 - self.cur)
+            self._bulk_region(0, self.cur)
         self._early_done = True
 
     def step(self):
@@ -354,7 +375,7 @@ class ShardedFlatAdam:
         else:
             first = 1 if self._early_done else 0
             for r in range(first, len(self.regions)):
-                self._fused_region(r, cur, nxt)
+                self._fused_region(r, cur, nxt, zero_all=self._early_done)   # (the bulk kernel of region 0 does not zero-fill)
             if self._early_done:
                 torch.cuda.current_stream(self.flat_param.device).wait_stream(self._side)
         self._early_done = False

@@ -331,6 +331,15 @@ int c2v_adam_step_sharded(const float *param_local, float *param_multicast, cons
                           float *zero_buffer, int64_t zero_n, float lr, float beta1, float beta2, float eps,
                           float weight_decay, int64_t step, float grad_scale, void *stream);
 
+/* The same sharded step for one slice, driven by bulk-async copies: one warp and 28 KB of shared memory per CTA, so that
+ * it fits on SMs that a persistent tensor-core kernel already occupies (used on a side stream for the gradients that are
+ * complete before the backward ends: ShardedFlatAdam.early_step).  Peer pointers only; no zero-fill.  max_ctas <= 0: one
+ * CTA per SM. */
+int c2v_adam_step_sharded_bulk(const float *param_local, float *const *param_peers, const float *const *grad_peers,
+                               int32_t world, float *exp_avg_slice, float *exp_avg_sq_slice, int64_t slice_begin,
+                               int64_t slice_n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                               int64_t step, float grad_scale, int32_t max_ctas, void *stream);
+
 /* ---- corpus reader / code-vector writer: the data formats either side of the path ----------
  * c2v_corpus_parse_*: DatasetReader.load (/root/reference/model/dataset_reader.py:72-128) for the `corpus.txt` format
  * (`#id`, `label:`, `class:`, `paths:` + `start\tpath\tend` lines, `vars:` + `original\talias` lines, blank line between
