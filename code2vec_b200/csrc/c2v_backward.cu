@@ -517,8 +517,10 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
                            const c2v_grads *g, void *ws, size_t ws_bytes, cudaStream_t st, const float *x_stash, int phase)
 {
     // phase 0: the whole backward.  Phases 1 / 2 split it where the path table's gradient is complete (all state between
-    // the two calls lives in the workspace): 1 = per-row work + dC of the path sub-vector, 2 = dC of start / end + dW.
-    // Only the tensor-core path with a stashed x splits; every other path does everything in phase 1.
+    // the two calls lives in the workspace): 1 = per-row work + dC of the path sub-vector + dW, 2 = dC of start / end.
+    // dW gathers rows of BOTH embedding tables, so it must run before a caller may start updating path_embedding between
+    // the phases; phase 2 reads only dx, the W^T image and the indices.  Only the tensor-core path with a stashed x
+    // splits; every other path does everything in phase 1.
     EncodeArgs a = a_in;
     if (a.H > 32 * MAXC) {
         set_error("encode backward supports encode_size <= %d (got %d)", 32 * MAXC, a.H);
@@ -543,10 +545,8 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
         if (phase == 2) {
             if (!split_ok) return C2V_OK;                       // phase 1 already did everything
             a.n_tiles = (int)((a.N + TM - 1) / TM);
-            int rc2 = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st,
-                                            5, false);
-            if (rc2 != C2V_OK) return rc2;
-            return launch_backward_dw_tc(a, dx, dx_absmax, g->input_linear, st);
+            return launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st,
+                                         5, false);
         }
         if (phase == 1 && !split_ok) phase = 0;
     }
@@ -591,8 +591,11 @@ int launch_encode_backward(const c2v_dims *d, const c2v_params *p, const EncodeA
         if (a.H <= 128) backward_rows_lite_kernel<1><<<sms * 16, 256, 0, st>>>(a, b);
         else backward_rows_lite_kernel<2><<<sms * 8, 256, 0, st>>>(a, b);
         C2V_LAUNCH_OK("backward_rows_lite_kernel");
-        if (phase == 1)                                         // path sub-vector only; start / end + dW follow in phase 2
-            return launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st, 2, true);
+        if (phase == 1) {                                       // path sub-vector + dW; start / end follow in phase 2
+            rc = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st, 2, true);
+            if (rc != C2V_OK) return rc;
+            return launch_backward_dw_tc(a, dx, dx_absmax, g->input_linear, st);
+        }
         rc = launch_backward_dc_tc(a, p->input_linear, dx, dx_absmax, dc_ws, g->terminal_embedding, g->path_embedding, st, 7, true);
         if (rc != C2V_OK) return rc;
         const char *dw_env2 = getenv("C2V_BACKWARD_DW");

@@ -246,8 +246,9 @@ int c2v_encode_backward_stashed(const c2v_dims *d, const c2v_params *p, const in
                                 const float *x_stash, const float *d_code_vector, const float *d_attention,
                                 const c2v_grads *grads, void *workspace, size_t workspace_bytes, void *stream);
 /* The same backward in two calls on the same workspace and gradient buffers (phase 0 = all at once = the call above):
- * phase 1 runs the per-row work and the path sub-vector of dC -- afterwards the gradient of path_embedding is complete --,
- * phase 2 the start / end sub-vectors (terminal_embedding) and dW (input_linear).  A data-parallel caller starts reducing
+ * phase 1 runs the per-row work, the path sub-vector of dC and dW -- afterwards the gradients of path_embedding and
+ * input_linear are complete and nothing reads the embedding tables any more --, phase 2 the start / end sub-vectors
+ * (terminal_embedding).  A data-parallel caller starts reducing
  * the path table between the two (ShardedFlatAdam.early_step).  Shapes that do not run on the tensor cores do
  * everything in phase 1. */
 int c2v_encode_backward_phased(const c2v_dims *d, const c2v_params *p, const int64_t *starts,
