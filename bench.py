@@ -267,7 +267,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--train-steps", type=int, default=8, help="also time K training steps (0 = skip)")
     ap.add_argument("--train-unfused-loss", action="store_true", help="training leg: forward() + eager loss instead of forward_loss()")
-    ap.add_argument("--no-early-reduce", action="store_true", help="training leg: reduce all gradients after the backward (no overlap)")
+    ap.add_argument("--early-reduce", action="store_true",
+                    help="training leg: reduce path_embedding's gradient on a side stream while the backward is still running "
+                         "(ShardedFlatAdam early region; experimental: slower today, see DESIGN.md section 5)")
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the ATen/cuBLAS eager comparator on this GPU")
     ap.add_argument("--transport", default="auto", choices=["auto", "nvls", "p2p", "nccl"],
                     help="gradient reduction of the training leg (ShardedFlatAdam)")
@@ -531,7 +533,7 @@ def main():
         model.load_state_dict(p)
         model = model.to(dev).train()
         optim = ShardedFlatAdam(model.parameters(), lr=0.01, betas=(0.9, 0.999), transport=args.transport,   # main.py:138
-                                early=[] if args.no_early_reduce else [model.path_embedding.weight])
+                                early=[model.path_embedding.weight] if args.early_reduce else [])
         # main.py:251-264: by default through Code2Vec.forward_loss (loss fused into the label GEMM, logits never written);
         # --train-unfused-loss: forward() + eager log_softmax + nll_loss on the [b, C] logits, like the reference's loop
         loss_fn = (lambda o_, l_: F.nll_loss(F.log_softmax(o_, dim=1), l_)) if args.train_unfused_loss else None

@@ -132,7 +132,7 @@ adam_step_sharded_kernel(const float *__restrict__ p_local, float *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// The same step driven by bulk-async copies (TMA) instead of thousands of threads: one warp per CTA, 28 KB of shared
+// The same step driven by bulk-async copies (TMA) instead of thousands of threads: four warps per CTA, 28 KB of shared
 // memory.  Purpose: run on a side stream NEXT TO the persistent tensor-core backward kernels, which own every SM
 // (22 warps x 72-80 registers, 197 KB of shared memory) and leave room for exactly this much -- the thread-per-element
 // kernel above cannot get enough CTAs resident beside them to keep NVLink busy.  Per chunk: lane 0 issues one
@@ -145,7 +145,9 @@ constexpr int AB_STAGES = 2, AB_STAGE_BYTES = 14 * 1024;
 
 __device__ __forceinline__ uint32_t ab_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(32)
+constexpr int AB_THREADS = 128;          // 4 warps x <= 48 registers = 6 K registers: fits beside the tensor-core backward kernels
+
+__global__ void __launch_bounds__(AB_THREADS)
 adam_step_bulk_kernel(const float *__restrict__ p_local, const AdamPeers peers, int world, float *__restrict__ m,
                       float *__restrict__ v, long long slice_begin, long long slice_n, int chunk,
                       float step_size, float one_minus_b1, float b2, float one_minus_b2, float inv_sqrt_bc2, float eps,
@@ -153,16 +155,16 @@ adam_step_bulk_kernel(const float *__restrict__ p_local, const AdamPeers peers, 
 {
     extern __shared__ __align__(128) unsigned char ab_raw[];
     __shared__ __align__(8) unsigned long long ab_bar[AB_STAGES];
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x;
     const long long n_chunks = (slice_n + chunk - 1) / chunk;
     const long long my_chunks = (n_chunks - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x;
-    if (lane == 0) {
+    if (tid == 0) {
         for (int s = 0; s < AB_STAGES; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ab_smem(&ab_bar[s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
-    auto issue = [&](long long k) {                               // lane 0: loads of this CTA's k-th chunk into stage k & 1
+    __syncthreads();
+    auto issue = [&](long long k) {                               // thread 0: loads of this CTA's k-th chunk into stage k & 1
         const long long c = (long long)blockIdx.x + k * gridDim.x;
         const long long off = c * chunk;
         const int len = (int)((slice_n - off) < chunk ? (slice_n - off) : chunk);
@@ -184,15 +186,24 @@ adam_step_bulk_kernel(const float *__restrict__ p_local, const AdamPeers peers, 
         const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
         pp = pp - step_size * (mm / denom);
     };
-    if (lane == 0 && my_chunks > 0) issue(0);
+    if (tid == 0 && my_chunks > 0) issue(0);
     for (long long k = 0; k < my_chunks; ++k) {
         const int st = (int)(k & 1);
-        if (lane == 0 && k + 1 < my_chunks) {
-            // the other stage's buffers were the source of chunk k-1's bulk stores: wait until those have READ them
+        if (tid == 0 && k + 1 < my_chunks) {
+            // the other stage's first buffer was the source of chunk k-1's bulk stores: wait until those have READ it
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             issue(k + 1);
         }
-        __syncwarp();
+        const long long c = (long long)blockIdx.x + k * gridDim.x;
+        const long long off = c * chunk;
+        const int len = (int)((slice_n - off) < chunk ? (slice_n - off) : chunk);
+        // p, m, v of this thread's first piece are local HBM: fetch them while the peers' gradients are still in flight
+        const int i0 = tid * 4;
+        float4 P0 = make_float4(0.f, 0.f, 0.f, 0.f), M0 = P0, V0 = P0;
+        if (i0 < len) {
+            P0 = *reinterpret_cast<const float4 *>(p_local + slice_begin + off + i0);
+            M0 = *reinterpret_cast<const float4 *>(m + off + i0); V0 = *reinterpret_cast<const float4 *>(v + off + i0);
+        }
         {   // wait for this stage's loads
             const uint32_t bar = ab_smem(&ab_bar[st]), parity = (uint32_t)(k >> 1) & 1u;
             uint32_t ok = 0;
@@ -201,26 +212,27 @@ adam_step_bulk_kernel(const float *__restrict__ p_local, const AdamPeers peers, 
                              : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
             }
         }
-        const long long c = (long long)blockIdx.x + k * gridDim.x;
-        const long long off = c * chunk;
-        const int len = (int)((slice_n - off) < chunk ? (slice_n - off) : chunk);
         float *stage = reinterpret_cast<float *>(ab_raw + (size_t)st * AB_STAGE_BYTES);
-        for (int i = lane * 4; i < len; i += 128) {               // len is a multiple of 4 (slices are)
+        for (int i = i0; i < len; i += 4 * AB_THREADS) {          // len is a multiple of 4 (slices are)
             float4 G = *reinterpret_cast<const float4 *>(stage + i);
             for (int r = 1; r < world; ++r) {                      // rank order: replicas of the sum are bit-identical
                 const float4 x = *reinterpret_cast<const float4 *>(stage + (size_t)r * chunk + i);
                 G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
             }
             const long long e = off + i;                           // offset inside the slice
-            float4 P = *reinterpret_cast<const float4 *>(p_local + slice_begin + e);
-            float4 M = *reinterpret_cast<const float4 *>(m + e), V = *reinterpret_cast<const float4 *>(v + e);
+            float4 P, M, V;
+            if (i == i0) { P = P0; M = M0; V = V0; }
+            else {
+                P = *reinterpret_cast<const float4 *>(p_local + slice_begin + e);
+                M = *reinterpret_cast<const float4 *>(m + e); V = *reinterpret_cast<const float4 *>(v + e);
+            }
             upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
             *reinterpret_cast<float4 *>(m + e) = M; *reinterpret_cast<float4 *>(v + e) = V;
             *reinterpret_cast<float4 *>(stage + i) = P;            // rank 0's buffer becomes the output staging
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the bulk stores
-        __syncwarp();
-        if (lane == 0) {
+        __syncthreads();
+        if (tid == 0) {
             const uint32_t src = ab_smem(stage), bytes = (uint32_t)len * 4u;
             for (int r = 0; r < world; ++r)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
@@ -228,8 +240,8 @@ adam_step_bulk_kernel(const float *__restrict__ p_local, const AdamPeers peers, 
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores performed before the kernel ends
-    __syncwarp();
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores performed before the kernel ends
+    __syncthreads();
     __threadfence_system();
 }
 
@@ -360,7 +372,7 @@ extern "C" int c2v_adam_step_sharded_bulk(const float *param_local, float *const
     if (grid > n_chunks) grid = n_chunks;
     const int smem = AB_STAGES * AB_STAGE_BYTES;
     C2V_CUDA_OK(cudaFuncSetAttribute(adam_step_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    adam_step_bulk_kernel<<<(unsigned)grid, 32, smem, static_cast<cudaStream_t>(stream)>>>(
+    adam_step_bulk_kernel<<<(unsigned)grid, AB_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
         param_local, peers, world, exp_avg_slice, exp_avg_sq_slice, slice_begin, slice_n, chunk, step_size, 1.0f - beta1, beta2,
         1.0f - beta2, inv_sqrt_bc2, eps, weight_decay, grad_scale);
     C2V_LAUNCH_OK("adam_step_bulk_kernel");
