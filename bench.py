@@ -428,6 +428,28 @@ def main():
                 "how": "CUDA events on the launch stream around every 8th launch of the kernel inside the timed passes "
                        "(launch + prologue inside the interval, no dependent-launch overlap for the bracketed launch)"}
 
+    # ---- the same kernel launched back to back (no bracketing events between launches, dependent-launch overlap intact):
+    #      what it costs the step, as opposed to what a bracketed launch shows; reported beside `frac`, not instead of it
+    def enc_only(i):
+        o = (i % nb) * B
+        _lib.check(lib.c2v_encode_forward(ctypes.byref(dims), ctypes.byref(params), P(s[o:o + B]), P(pth[o:o + B]),
+                                          P(e[o:o + B]), B, L, None, P(cv), P(att), P(ws), ws_n, algo | REUSE, st), "encode")
+    n_b2b = 256
+    for i in range(8):
+        enc_only(i)
+    torch.cuda.synchronize(dev)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(stream)
+    for i in range(n_b2b):
+        enc_only(8 + i)
+    b1.record(stream)
+    torch.cuda.synchronize(dev)
+    b2b_ms = b0.elapsed_time(b1) / n_b2b                       # encode kernel + its 4 us finalize kernel per call
+    roofline["encode_call_ms_back_to_back"] = b2b_ms
+    roofline["frac_back_to_back"] = alg_bytes / (b2b_ms * 1e-3) / 1e9 / peak
+    roofline["back_to_back_note"] = (f"{n_b2b} c2v_encode_forward calls (encode_tm_kernel + encode_finalize_kernel) between two CUDA events, "
+                                     "no events in between; includes the finalize kernel, so it is an upper bound of the kernel's own time")
+
     # ---- the same path on the existing Blackwell kernels: ATen/cuBLAS eager on this GPU ----------
     gpu_eager = None
     if rank == 0 and not args.no_gpu_eager:
