@@ -85,8 +85,8 @@ adam_step_sharded_kernel(const float *__restrict__ p_local, float *__restrict__ 
         const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
         pp = pp - step_size * (mm / denom);
     };
-    // Every 4th CTA only zero-fills the other gradient bucket (local HBM stores), the rest do the NVLink work, four 16-byte
-    // gradient loads per thread issued before any is consumed, so that enough bytes are in flight per SM (the in-switch reduction has a
+    // Every 4th CTA only zero-fills the other gradient bucket (local HBM stores), the rest do the NVLink work, two 16-byte
+    // pieces per thread and iteration so that twice the bytes are in flight per thread (the in-switch reduction has a
     // round trip of several microseconds): both halves of the step run side by side instead of one after the other.
     const int n_zero_cta = zero_n4 > 0 ? (int)gridDim.x / 4 : 0;
     const bool zero_role = n_zero_cta > 0 && (blockIdx.x & 3) == 3;
@@ -98,34 +98,34 @@ adam_step_sharded_kernel(const float *__restrict__ p_local, float *__restrict__ 
     }
     const int wb = (int)blockIdx.x - (n_zero_cta > 0 ? (int)(blockIdx.x + 1) / 4 : 0);
     const long long stride = (long long)((int)gridDim.x - n_zero_cta) * blockDim.x, t0 = (long long)wb * blockDim.x + threadIdx.x;
-    constexpr int U = 4;                                          // pieces in flight per thread
-    for (long long i0 = t0; i0 < slice_n4; i0 += U * stride) {
-        float4 G[U];
-        long long idx[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {                              // all gradient loads (NVLink round trips) first
-            idx[u] = i0 + u * stride;
-            const bool on = idx[u] < slice_n4;
-            const long long e = slice_begin + 4 * (on ? idx[u] : i0);
-            if (MULTIMEM) G[u] = mm_ld_reduce_add(g_mc + e);
-            else {
-                G[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int r = 0; r < world; ++r) {                   // fixed rank order: every replica of the sum is bit-identical
-                    const float4 x = *reinterpret_cast<const float4 *>(peers.grad[r] + e);
-                    G[u].x += x.x; G[u].y += x.y; G[u].z += x.z; G[u].w += x.w;
-                }
+    for (long long i0 = t0; i0 < slice_n4; i0 += 2 * stride) {
+        const long long i1 = i0 + stride;
+        const bool two = i1 < slice_n4;
+        const long long e0 = slice_begin + 4 * i0, e1 = slice_begin + 4 * (two ? i1 : i0);   // element offsets in the flat buffers
+        float4 G0, G1;
+        if (MULTIMEM) { G0 = mm_ld_reduce_add(g_mc + e0); G1 = two ? mm_ld_reduce_add(g_mc + e1) : G0; }
+        else {
+            G0 = G1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < world; ++r) {                   // fixed rank order: every replica of the sum is bit-identical
+                const float4 x0 = *reinterpret_cast<const float4 *>(peers.grad[r] + e0);
+                const float4 x1 = *reinterpret_cast<const float4 *>(peers.grad[r] + e1);
+                G0.x += x0.x; G0.y += x0.y; G0.z += x0.z; G0.w += x0.w;
+                G1.x += x1.x; G1.y += x1.y; G1.z += x1.z; G1.w += x1.w;
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (idx[u] >= slice_n4) break;
-            const long long e = slice_begin + 4 * idx[u];           // element offset in the flat buffers
-            float4 P = *reinterpret_cast<const float4 *>(p_local + e), M = m[idx[u]], V = v[idx[u]];
-            upd(P.x, G[u].x, M.x, V.x); upd(P.y, G[u].y, M.y, V.y); upd(P.z, G[u].z, M.z, V.z); upd(P.w, G[u].w, M.w, V.w);
-            m[idx[u]] = M; v[idx[u]] = V;
-            if (MULTIMEM) mm_st(p_mc + e, P);
+        float4 P0 = *reinterpret_cast<const float4 *>(p_local + e0), M0 = m[i0], V0 = v[i0];
+        float4 P1 = *reinterpret_cast<const float4 *>(p_local + e1), M1 = m[two ? i1 : i0], V1 = v[two ? i1 : i0];
+        upd(P0.x, G0.x, M0.x, V0.x); upd(P0.y, G0.y, M0.y, V0.y); upd(P0.z, G0.z, M0.z, V0.z); upd(P0.w, G0.w, M0.w, V0.w);
+        m[i0] = M0; v[i0] = V0;
+        if (MULTIMEM) mm_st(p_mc + e0, P0);
+        else
+            for (int r = 0; r < world; ++r) *reinterpret_cast<float4 *>(peers.param[r] + e0) = P0;
+        if (two) {
+            upd(P1.x, G1.x, M1.x, V1.x); upd(P1.y, G1.y, M1.y, V1.y); upd(P1.z, G1.z, M1.z, V1.z); upd(P1.w, G1.w, M1.w, V1.w);
+            m[i1] = M1; v[i1] = V1;
+            if (MULTIMEM) mm_st(p_mc + e1, P1);
             else
-                for (int r = 0; r < world; ++r) *reinterpret_cast<float4 *>(peers.param[r] + e) = P;
+                for (int r = 0; r < world; ++r) *reinterpret_cast<float4 *>(peers.param[r] + e1) = P1;
         }
     }
     __threadfence_system();
