@@ -1,5 +1,5 @@
 // c2v_backward_dc_tc.cu -- K3c: dC = dX . W on the tensor cores + scatter into the embedding gradients
-// (terminal_embed = path_embed = E <= 128, encode = H <= 128, multiples of 4; zero-padded to 128 inside the panels).
+// (terminal_embed = path_embed = E <= 256, encode = H <= 256, multiples of 4; zero-padded to 128 inside the panels).
 //
 // The gradient of the gathered context vectors (autograd of model.py:48-54 under loss.backward(), main.py:174):
 //   dC[r, d] = sum_h dX[r, h] * W[h, d],  then  dE_t[starts_r] += dC[r, 0:128], dE_p[paths_r] += dC[r, 128:256],
@@ -13,6 +13,10 @@
 // Warps: 0-3 scatter epilogue (thread = context row: tcgen05.ld -> 128-bit atomics into the three embedding rows) |
 // 4-19 dX producers | 20 MMA issuer | 21 W^T producer.  The three accumulators are released one by one, so the scatter
 // of sub-vector sv overlaps the MMAs of sv+1 (and of the next tile).
+// Sizes above 128: blockIdx.y = db selects the 128-wide window of d inside every sub-vector (its own grid of CTAs over the
+// row tiles); the contraction over h runs as n_hb blocks of 128 through the same operand stages, accumulating in tensor
+// memory, and the accumulator is handed to the scatter warps after the last block -- so every dC element is still added
+// to the embedding gradient exactly once.
 #include <cuda_fp16.h>
 
 #include "c2v_tc_ptx.cuh"
@@ -34,8 +38,9 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t
 constexpr int IMG_BYTES = NB * B_SLOT;                // 192 KB
 }  // namespace dct
 
-// W [H=128][D=384] fp32 -> 6 tiles (sv * 2 + kb) of {hi, lo} [128 d x 64 h] fp16, K-major SWIZZLE_128B, scaled by the
-// power of two that lifts max |W| (bits in *absmax_bits, found by wt_absmax_kernel) just below 2^14.
+// W [H][D = 3E] fp32 -> per (db, hb) window pair 6 tiles (sv * 2 + kb) of {hi, lo} [128 d x 64 h] fp16, K-major
+// SWIZZLE_128B (d = 128 db + row, h = 128 hb + 64 kb + column; zeros beyond E / H), scaled by the power of two that lifts
+// max |W| (bits in *absmax_bits, found by wt_absmax_kernel) just below 2^14.  Image order: [db][hb][sv][kb].
 __global__ void wt_absmax_kernel(const float *__restrict__ W, int n, unsigned *__restrict__ absmax_bits)
 {
     float m = 0.0f;
@@ -44,7 +49,7 @@ __global__ void wt_absmax_kernel(const float *__restrict__ W, int n, unsigned *_
     if ((threadIdx.x & 31) == 0) atomicMax(absmax_bits, __float_as_uint(m));
 }
 __global__ void __launch_bounds__(256)
-split_wt_kernel(const float *__restrict__ W, int H, int E, const unsigned *__restrict__ absmax_bits,
+split_wt_kernel(const float *__restrict__ W, int H, int E, int n_hb, int n_db, const unsigned *__restrict__ absmax_bits,
                 uint8_t *__restrict__ img, float *__restrict__ hdr)
 {
     const float mx = __uint_as_float(*absmax_bits);
@@ -57,15 +62,19 @@ split_wt_kernel(const float *__restrict__ W, int H, int E, const unsigned *__res
         scale = ldexpf(1.0f, k);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { hdr[0] = 1.0f / scale; hdr[1] = scale; }
-    // one thread = 4 consecutive d of one h of the PADDED [128 h][3 x 128 d] matrix (zeros beyond H / E); coalesced 16-B
-    // reads of W's rows ([H][3E] row-major)
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < dct::H * dct::D / 4; g += gridDim.x * blockDim.x) {
-        const int h = g / (dct::D / 4), dp = (g % (dct::D / 4)) * 4;
-        const int sv = dp / dct::E, dl = dp % dct::E, kb = h / 64, kk = h % 64;
+    // one thread = 4 consecutive d of one h of one window pair's PADDED [128 h][3 x 128 d] matrix (zeros beyond H / E);
+    // coalesced 16-B reads of W's rows ([H][3E] row-major)
+    constexpr int PER_WIN = dct::H * dct::D / 4;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_db * n_hb * PER_WIN; g += gridDim.x * blockDim.x) {
+        const int win = g / PER_WIN, gw = g % PER_WIN;      // win = db * n_hb + hb
+        const int db = win / n_hb, hb = win % n_hb;
+        const int hl = gw / (dct::D / 4), dp = (gw % (dct::D / 4)) * 4;
+        const int sv = dp / dct::E, dl = dp % dct::E, kb = hl / 64, kk = hl % 64;
+        const int h = hb * dct::H + hl, d = db * dct::E + dl;
         float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (h < H && dl < E) w4 = *reinterpret_cast<const float4 *>(W + (size_t)h * (3 * E) + sv * E + dl);
+        if (h < H && d < E) w4 = *reinterpret_cast<const float4 *>(W + (size_t)h * (3 * E) + sv * E + d);
         const float wv[4] = {w4.x * scale, w4.y * scale, w4.z * scale, w4.w * scale};
-        uint8_t *base = img + (size_t)(sv * 2 + kb) * dct::B_SLOT;
+        uint8_t *base = img + ((size_t)win * dct::NB + sv * 2 + kb) * dct::B_SLOT;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const __half hi = __float2half_rn(wv[q]);
@@ -80,13 +89,13 @@ split_wt_kernel(const float *__restrict__ W, int H, int E, const unsigned *__res
 __global__ void __launch_bounds__(dct::THREADS, 1)
 backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const unsigned *__restrict__ dx_absmax,
                       const uint8_t *__restrict__ wt_img, const float *__restrict__ wt_hdr,
-                      float *__restrict__ g_emb_t, float *__restrict__ g_emb_p, const int sv_mask)
+                      float *__restrict__ g_emb_t, float *__restrict__ g_emb_p, const int sv_mask, const int n_hb)
 {
+    const int db = (int)blockIdx.y;                     // this CTA's 128-wide window of d inside every sub-vector
     // sv_mask: which sub-vectors (bit 0 start, 1 path, 2 end) this launch handles.  The training step runs the path
     // sub-vector first (mask 2): the path table's gradient is then complete and its data-parallel reduction can overlap
     // the start / end launch (mask 5) -- see ShardedFlatAdam.early_step.
     const int last_sv = (sv_mask & 4) ? 2 : ((sv_mask & 2) ? 1 : 0);
-    const int n_sv = ((sv_mask >> 0) & 1) + ((sv_mask >> 1) & 1) + ((sv_mask >> 2) & 1);
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -144,20 +153,22 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
         }
         const float4 *dx4 = reinterpret_cast<const float4 *>(dx);
         const int H4 = a.H / 4;
-        for (int tl = 0; tl < my_tiles; ++tl) {
+        for (int vt = 0; vt < my_tiles * n_hb; ++vt) {                 // vt = (row tile, h block): one operand stage each
+            const int tl = vt / n_hb, h04 = (vt % n_hb) * 32;          // h block start in 16-byte pieces
             const long long row0 = ((long long)blockIdx.x + (long long)tl * gridDim.x) * dct::ROWS + pw * dct::ROWS_PER_PW;
-            const int as = tl & 1;
+            const int as = vt & 1;
             float4 buf[2][4];
 #pragma unroll
             for (int p = 0; p < 2; ++p)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const long long r = row0 + 2 * j + sub_row;
-                    float4 v = (r < a.N && p * 16 + q < H4) ? ldg_nc_v4(dx4 + (size_t)r * H4 + p * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = (r < a.N && h04 + p * 16 + q < H4) ? ldg_nc_v4(dx4 + (size_t)r * H4 + h04 + p * 16 + q)
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                     v.x *= dx_scale; v.y *= dx_scale; v.z *= dx_scale; v.w *= dx_scale;
                     buf[p][j] = v;
                 }
-            mbar_wait(bar_aempty + 8 * as, (((uint32_t)(tl >> 1)) & 1u) ^ 1u, status);
+            mbar_wait(bar_aempty + 8 * as, (((uint32_t)(vt >> 1)) & 1u) ^ 1u, status);
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 const uint32_t hi = base + dct::SMEM_A_OFF + as * dct::A_STAGE + p * dct::PANEL, lo = hi + 2 * dct::PANEL;
@@ -179,28 +190,31 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
     } else if (warp == dct::W_WARP) {
         // =============================== W^T PRODUCER ===============================
         if (lane == 0) {
-            const int n_items = my_tiles * 2 * n_sv;
-            int kb6 = 0;
-            while (!((sv_mask >> (kb6 >> 1)) & 1)) kb6 += 2;                 // first active sub-vector
-            for (int it = 0; it < n_items; ++it) {
-                const int bs = it & 1;
-                mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(it >> 1)) & 1u) ^ 1u, status);
-                mbar_arrive_expect_tx(bar_bfull + 8 * bs, dct::B_SLOT);
-                bulk_copy_g2s(base + dct::SMEM_B_OFF + bs * dct::B_SLOT, wt_img + (size_t)kb6 * dct::B_SLOT, dct::B_SLOT, bar_bfull + 8 * bs);
-                do { if (++kb6 == dct::NB) kb6 = 0; } while (!((sv_mask >> (kb6 >> 1)) & 1));
+            int it = 0;                                  // same (row tile, h block, sub-vector, k-block) order as the MMA warp
+            for (int vt = 0; vt < my_tiles * n_hb; ++vt) {
+                const uint8_t *win = wt_img + (size_t)(db * n_hb + vt % n_hb) * dct::IMG_BYTES;
+                for (int kb6 = 0; kb6 < dct::NB; ++kb6) {
+                    if (!((sv_mask >> (kb6 >> 1)) & 1)) continue;
+                    const int bs = it & 1;
+                    mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(it >> 1)) & 1u) ^ 1u, status);
+                    mbar_arrive_expect_tx(bar_bfull + 8 * bs, dct::B_SLOT);
+                    bulk_copy_g2s(base + dct::SMEM_B_OFF + bs * dct::B_SLOT, win + (size_t)kb6 * dct::B_SLOT, dct::B_SLOT, bar_bfull + 8 * bs);
+                    ++it;
+                }
             }
         }
         __syncwarp();
     } else if (warp == dct::MMA_WARP) {
         // =============================== MMA ISSUER (converged, one elected lane) ===============================
         int it = 0;
-        for (int tl = 0; tl < my_tiles; ++tl) {
-            const int as = tl & 1;
-            mbar_wait(bar_afull + 8 * as, ((uint32_t)(tl >> 1)) & 1u, status);
+        for (int vt = 0; vt < my_tiles * n_hb; ++vt) {
+            const int tl = vt / n_hb, hb = vt % n_hb;
+            const int as = vt & 1;
+            mbar_wait(bar_afull + 8 * as, ((uint32_t)(vt >> 1)) & 1u, status);
 #pragma unroll 1
             for (int sv = 0; sv < 3; ++sv) {
                 if (!((sv_mask >> sv) & 1)) continue;
-                mbar_wait(bar_tempty + 8 * sv, ((uint32_t)tl & 1u) ^ 1u, status);      // scatter of the previous tile drained
+                if (hb == 0) mbar_wait(bar_tempty + 8 * sv, ((uint32_t)tl & 1u) ^ 1u, status);   // scatter of the previous tile drained
 #pragma unroll 1
                 for (int kb = 0; kb < 2; ++kb, ++it) {
                     const int bs = it & 1;
@@ -215,13 +229,13 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t a_hi = umma_desc(sa + k * 32), a_lo = umma_desc(sa + 2 * dct::PANEL + k * 32);
                             const uint64_t b_hi = umma_desc(sb + k * 32), b_lo = umma_desc(sb + dct::PANEL + k * 32);
-                            umma_f16(d_tmem, a_hi, b_hi, dct::IDESC, (kb | k) != 0 ? 1u : 0u);
+                            umma_f16(d_tmem, a_hi, b_hi, dct::IDESC, (hb | kb | k) != 0 ? 1u : 0u);
                             umma_f16(d_tmem, a_lo, b_hi, dct::IDESC, 1u);
                             umma_f16(d_tmem, a_hi, b_lo, dct::IDESC, 1u);
                         }
                         umma_commit(bar_bempty + 8 * bs);
                         if (kb == 1) {
-                            umma_commit(bar_tfull + 8 * sv);
+                            if (hb == n_hb - 1) umma_commit(bar_tfull + 8 * sv);          // contraction over all of h complete
                             if (sv == last_sv) umma_commit(bar_aempty + 8 * as);
                         }
                     }
@@ -243,7 +257,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 #pragma unroll 1
             for (int sv = 0; sv < 3; ++sv) {
                 if (!((sv_mask >> sv) & 1)) continue;
-                float *dst = sv == 1 ? g_emb_p + (size_t)ip * a.Et : g_emb_t + (size_t)(sv == 0 ? is : ie) * a.Et;
+                float *dst = (sv == 1 ? g_emb_p + (size_t)ip * a.Et : g_emb_t + (size_t)(sv == 0 ? is : ie) * a.Et) + db * dct::E;
                 mbar_wait(bar_tfull + 8 * sv, (uint32_t)tl & 1u, status);
                 tc_fence_after();
 #pragma unroll 1
@@ -260,7 +274,7 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float v0 = v[j] * inv, v1 = v[j + 1] * inv, v2 = v[j + 2] * inv, v3 = v[j + 3] * inv;
-                            if (c * 32 + j < a.Et && (v0 != 0.0f || v1 != 0.0f || v2 != 0.0f || v3 != 0.0f))   // padded contexts: dx == 0
+                            if (db * dct::E + c * 32 + j < a.Et && (v0 != 0.0f || v1 != 0.0f || v2 != 0.0f || v3 != 0.0f))   // padded contexts: dx == 0
                                 red_add_v4(dst + c * 32 + j, make_float4(v0, v1, v2, v3));
                         }
                     }
@@ -277,11 +291,11 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 }
 
 bool backward_dc_tc_ok(const EncodeArgs &a) {
-    return a.Et == a.Ep && a.Et <= dct::E && a.H <= dct::H && (a.Et & 3) == 0 && (a.H & 3) == 0;
+    return a.Et == a.Ep && a.Et <= 2 * dct::E && a.H <= 2 * dct::H && (a.Et & 3) == 0 && (a.H & 3) == 0;
 }
-size_t backward_dc_tc_workspace_bytes() { return 1024 + dct::IMG_BYTES; }
+size_t backward_dc_tc_workspace_bytes() { return 1024 + 4 * dct::IMG_BYTES; }      // up to 2 x 2 window pairs
 
-// ws: [0, 1024) header {1/scale, scale} | W^T image
+// ws: [0, 1024) header {1/scale, scale} | W^T images [db][hb]
 int launch_backward_dc_tc(const EncodeArgs &a_in, const float *W, const float *dx, const unsigned *dx_absmax, void *ws,
                           float *g_emb_t, float *g_emb_p, cudaStream_t st, int sv_mask, bool build_image)
 {
@@ -289,12 +303,13 @@ int launch_backward_dc_tc(const EncodeArgs &a_in, const float *W, const float *d
     a.n_tiles = (int)((a.N + dct::ROWS - 1) / dct::ROWS);
     float *hdr = static_cast<float *>(ws);
     uint8_t *img = static_cast<uint8_t *>(ws) + 1024;
+    const int n_hb = (a.H + dct::H - 1) / dct::H, n_db = (a.Et + dct::E - 1) / dct::E;
     unsigned *mxbits = reinterpret_cast<unsigned *>(static_cast<uint8_t *>(ws) + 512);
     if (build_image) {
         C2V_CUDA_OK(cudaMemsetAsync(mxbits, 0, 4, st));
         wt_absmax_kernel<<<48, 256, 0, st>>>(W, a.H * a.D, mxbits);
         C2V_LAUNCH_OK("wt_absmax_kernel");
-        split_wt_kernel<<<48, 256, 0, st>>>(W, a.H, a.Et, mxbits, img, hdr);
+        split_wt_kernel<<<48 * n_hb * n_db, 256, 0, st>>>(W, a.H, a.Et, n_hb, n_db, mxbits, img, hdr);
         C2V_LAUNCH_OK("split_wt_kernel");
     }
     if ((sv_mask & 7) == 0) return C2V_OK;
@@ -302,9 +317,11 @@ int launch_backward_dc_tc(const EncodeArgs &a_in, const float *W, const float *d
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     C2V_CUDA_OK(cudaFuncSetAttribute(backward_dc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dct::SMEM_BYTES));
-    int grid = a.n_tiles < sms ? a.n_tiles : sms;
+    int grid = sms / n_db;                                 // one CTA per SM over the d windows
+    if (grid > a.n_tiles) grid = a.n_tiles;
     if (grid < 1) grid = 1;
-    backward_dc_tc_kernel<<<grid, dct::THREADS, dct::SMEM_BYTES, st>>>(a, dx, dx_absmax, img, hdr, g_emb_t, g_emb_p, sv_mask & 7);
+    backward_dc_tc_kernel<<<dim3(grid, n_db), dct::THREADS, dct::SMEM_BYTES, st>>>(a, dx, dx_absmax, img, hdr, g_emb_t, g_emb_p,
+                                                                                sv_mask & 7, n_hb);
     C2V_LAUNCH_OK("backward_dc_tc_kernel");
     return C2V_OK;
 }

@@ -1,5 +1,6 @@
-// c2v_backward_dw_tc.cu -- K3b: dW = dX^T . C on the tensor cores (terminal_embed = path_embed = E <= 128, encode = H <= 128,
-// both multiples of 4: the reference's default 100/100/100 runs here with the panels zero-padded to 128).
+// c2v_backward_dw_tc.cu -- K3b: dW = dX^T . C on the tensor cores (terminal_embed = path_embed = E <= 256, encode = H <= 256,
+// both multiples of 4: the reference's default 100/100/100 runs here with the panels zero-padded to 128; sizes above 128
+// run as 128-wide windows of h and of d, one window pair per blockIdx.y -- see "windows" below).
 //
 // The weight gradient of input_linear (what autograd computes for model.py:54 under loss.backward(), main.py:174):
 //   dW[h, d] = sum over context rows r of dX[r, h] * C[r, d],   C[r] = [E_t[s_r]; E_p[p_r]; E_t[e_r]]
@@ -16,6 +17,9 @@
 // Warps: 0-3 final reduction | 4-19 producers (8 rows each: LDG.128 -> hi/lo split -> STS.64) | 20 MMA issuer.
 // smem: 2 tile-stages of the dX operand {hi p0, hi p1, lo p0, lo p1} (128 KB) + 2 slots of one gathered panel {hi, lo}
 // (64 KB); per tile 6 gathered panels (start / path / end x 2 halves) stream through the slots: 144 MMAs (N = 64).
+// Windows: blockIdx.y = hb * n_db + db selects rows h in [128 hb, 128 hb + 128) of dW and, inside each of the three
+// sub-vectors, columns d in [128 db, 128 db + 128); the CTAs of one window pair (gridDim.x of them) share the row tiles.
+// At E = H = 256 that is four window pairs: dX and the gathered rows are each read twice, the MMAs are the same 2 H D.
 #include <cuda_fp16.h>
 
 #include "c2v_tc_ptx.cuh"
@@ -45,8 +49,9 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t lbo_by
 
 __global__ void __launch_bounds__(dwt::THREADS, 1)
 backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const unsigned *__restrict__ dx_absmax,
-                      float *__restrict__ dW)
+                      float *__restrict__ dW, const int n_db)
 {
+    const int hb = (int)blockIdx.y / n_db, db = (int)blockIdx.y % n_db;       // this CTA's 128-wide windows of h and of d
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -117,6 +122,7 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
             }
         };
         const int E4 = a.Et / 4, H4 = a.H / 4;        // row lengths in 16-byte pieces (columns beyond them are zero padding)
+        const int h04 = hb * 32, d04 = db * 32;       // window starts, in 16-byte pieces
         const float4 *tab_t = reinterpret_cast<const float4 *>(a.emb_t);
         const float4 *tab_p = reinterpret_cast<const float4 *>(a.emb_p);
         const float4 *dx4 = reinterpret_cast<const float4 *>(dx);
@@ -140,7 +146,8 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const long long r = row0 + 2 * j + sub_row;
-                    buf[j] = (r < a.N && p * 16 + q < H4) ? ldg_nc_v4(dx4 + (size_t)r * H4 + p * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    buf[j] = (r < a.N && h04 + p * 16 + q < H4) ? ldg_nc_v4(dx4 + (size_t)r * H4 + h04 + p * 16 + q)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
                     buf[j].x *= dx_scale; buf[j].y *= dx_scale; buf[j].z *= dx_scale; buf[j].w *= dx_scale;
                 }
                 const uint32_t hi = base + dwt::SMEM_A_OFF + as * dwt::A_STAGE + p * dwt::PANEL;
@@ -160,7 +167,8 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t o = __shfl_sync(0xffffffffu, off, 2 * j + sub_row);
                     const long long r = row0 + 2 * j + sub_row;
-                    buf[j] = (r < a.N && (kb & 1) * 16 + q < E4) ? ldg_nc_v4(tab + (size_t)o + (kb & 1) * 16 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    buf[j] = (r < a.N && d04 + (kb & 1) * 16 + q < E4) ? ldg_nc_v4(tab + (size_t)o + d04 + (kb & 1) * 16 + q)
+                                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 const int bs = itb & 1;
                 mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(itb >> 1)) & 1u) ^ 1u, status);
@@ -212,16 +220,16 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
         // thread = row h of dW (TMEM lane); 384 accumulator columns = d; added to the global gradient with 128-bit atomics
         mbar_wait(bar_acc, 0u, status);
         tc_fence_after();
-        const int h = warp * 32 + lane;
+        const int h = hb * 128 + warp * 32 + lane;
         const float inv = 1.0f / dx_scale;
         const int E = a.Et;
-        float *dst = dW + (size_t)h * (3 * E);                 // dW is [H][3E]; accumulator column sv * 128 + d
+        float *dst = dW + (size_t)h * (3 * E);                 // dW is [H][3E]; accumulator column sv * 128 + (d - 128 db)
 #pragma unroll 1
         for (int c = 0; c < dwt::D / 32; ++c) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
             tmem_ld_wait();
-            const int sv = c >> 2, d0 = (c & 3) * 32;
+            const int sv = c >> 2, d0 = db * 128 + (c & 3) * 32;
             if (h < a.H) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -240,7 +248,7 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 }
 
 bool backward_dw_tc_ok(const EncodeArgs &a) {
-    return a.Et == a.Ep && a.Et <= dwt::E && a.H <= dwt::H && (a.Et & 3) == 0 && (a.H & 3) == 0 &&
+    return a.Et == a.Ep && a.Et <= 2 * dwt::E && a.H <= 2 * dwt::H && (a.Et & 3) == 0 && (a.H & 3) == 0 &&
            (long long)a.T * a.Et * 4 < (1ll << 32) && (long long)a.P * a.Et * 4 < (1ll << 32);
 }
 
@@ -252,9 +260,11 @@ int launch_backward_dw_tc(const EncodeArgs &a_in, const float *dx, const unsigne
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     C2V_CUDA_OK(cudaFuncSetAttribute(backward_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dwt::SMEM_BYTES));
-    int grid = a.n_tiles < sms ? a.n_tiles : sms;
+    const int n_hb = (a.H + dwt::H - 1) / dwt::H, n_db = (a.Et + dwt::E - 1) / dwt::E;
+    int grid = sms / (n_hb * n_db);                        // one CTA per SM over all window pairs
+    if (grid > a.n_tiles) grid = a.n_tiles;
     if (grid < 1) grid = 1;
-    backward_dw_tc_kernel<<<grid, dwt::THREADS, dwt::SMEM_BYTES, st>>>(a, dx, dx_absmax, dW);
+    backward_dw_tc_kernel<<<dim3(grid, n_hb * n_db), dwt::THREADS, dwt::SMEM_BYTES, st>>>(a, dx, dx_absmax, dW, n_db);
     C2V_LAUNCH_OK("backward_dw_tc_kernel");
     return C2V_OK;
 }

@@ -9,6 +9,7 @@ by running the UNMODIFIED reference (imported from /root/reference, never copied
   tests/golden/builder_vars.npz   reference DatasetBuilder.build_data, infer_variable branch (dataset_builder.py:152-204)
   tests/golden/writer.npz         reference write_code_vectors (main.py:393-423) output for fixed vectors
   tests/golden/unaligned.npz, grad_unaligned.npz   forward / gradient goldens with embed / encode sizes not divisible by 4
+  tests/golden/grad_wide.npz, grad_e200.npz        gradient goldens with embed / encode sizes above 128
 """
 import ast
 import hashlib
@@ -183,3 +184,6 @@ if __name__ == "__main__":
     gg.seeded("unaligned", 21, 6, 9, 23, 17, 5, 10, 7, 9, holes=True, allpad_rows=(3,))
     gg.seeded("grad_unaligned", 22, 5, 11, 23, 17, 5, 10, 7, 9, grads=True, holes=True, allpad_rows=(2,))
     gg.seeded("grad_e50", 23, 3, 12, 40, 30, 6, 50, 50, 50, grads=True)
+    # embed / encode sizes above 128: the tensor-core backward runs them as 128-wide windows (c2v_backward_d{w,c}_tc.cu)
+    gg.seeded("grad_wide", 24, 5, 70, 80, 60, 12, 256, 256, 256, grads=True, allpad_rows=(3,))
+    gg.seeded("grad_e200", 25, 4, 60, 90, 70, 10, 200, 200, 192, grads=True, holes=True)

@@ -156,14 +156,15 @@ def test_one_adam_step_matches_reference_training_semantics():
         assert np.quantile(d, 0.999) <= 2e-4, k
 
 
-def test_tensor_core_dw_matches_the_cuda_core_gemm_at_many_tiles_per_cta():
+@pytest.mark.parametrize("E,H,B", [(128, 128, 256), (256, 256, 160), (200, 192, 40), (128, 256, 40), (256, 128, 40), (132, 100, 24)])
+def test_tensor_core_dw_matches_the_cuda_core_gemm_at_many_tiles_per_cta(E, H, B):
     """K3b (dW = dX^T . C on tcgen05, MN-major operands) and K3c (dC = dX . W + scatter into the embedding gradients)
-    against the CUDA-core kernels on 51,200 context rows = 400
-    tiles (every CTA walks several tiles: operand stage / ring reuse and the TMEM-resident partial), ragged bags and an
-    all-pad bag included; and against the fp64 product of the same dX on a slice of rows."""
+    against the CUDA-core kernels on up to 51,200 context rows = 400 tiles (every CTA walks several tiles: operand stage /
+    ring reuse and the TMEM-resident partial), ragged bags and an all-pad bag included.  Sizes above 128 run as 128-wide
+    windows of h and d (dW: one window pair per blockIdx.y; dC: the contraction over h in blocks through tensor memory)."""
     import os
     rng = np.random.default_rng(13)
-    T, P, C, E, H, B, L = 3000, 2000, 16, 128, 128, 256, 200
+    T, P, C, L = 3000, 2000, 16, 200
     p = random_params(rng, T, P, C, E, E, H)
     starts, paths, ends, label = random_batch(rng, B, L, T, P, C)
     starts[7, :] = 0
