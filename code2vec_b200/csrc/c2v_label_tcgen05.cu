@@ -109,7 +109,29 @@ __device__ __forceinline__ float lt_from_orderable(uint32_t k) {
 // tiles then write adjacent 512-B pieces of the same 128 output rows within a few microseconds (L2 merges them into
 // long DRAM bursts: with n-tile-major order the label GEMM wrote at 2.2 TB/s, with contiguous 4 KB runs at 4.2 TB/s),
 // and the W_out tiles of a group (NT_GROUP x 64 KB) are re-read from L2 by the n_mt m-tiles.
+// Lane order (per_m > 0, what the launcher picks whenever n_mt * per_m CTAs cover >= 95 % of the SMs): CTA c owns m-tile
+// c % n_mt for the whole launch and walks the n-tiles of slice c / n_mt of the label range one after the other.  The n_mt
+// CTAs of a slice (adjacent CTA ids, same pace) ask for the same W_out tile within a few microseconds: one DRAM read and
+// n_mt - 1 L2 hits, where the group order re-read the whole 100 MB image n_mt times at C = 195,299 (the 800 MB of streaming
+// logits evict a group's tiles between a CTA's visits: 809 MB read per launch under ncu); and every CTA extends each of its
+// 128 output rows by 512 contiguous bytes per tile.
 struct LtTile { long long nt; int mt; };
+struct LtRange { long long t_lo; int my_tiles; int mt; };         // lane order: t_lo = first n-tile, mt fixed; group order: mt = -1
+__device__ __forceinline__ LtRange lt_range(long long n_tiles, int n_mt, long long n_nt, int per_m) {
+    LtRange r;
+    if (per_m > 0) {
+        const int slice = (int)blockIdx.x / n_mt;
+        r.mt = (int)blockIdx.x % n_mt;
+        if (slice >= per_m) { r.t_lo = 0; r.my_tiles = 0; return r; }
+        r.t_lo = n_nt * slice / per_m;
+        r.my_tiles = (int)(n_nt * (slice + 1) / per_m - r.t_lo);
+        return r;
+    }
+    r.mt = -1;
+    r.t_lo = n_tiles * blockIdx.x / gridDim.x;
+    r.my_tiles = (int)(n_tiles * (blockIdx.x + 1) / gridDim.x - r.t_lo);
+    return r;
+}
 __device__ __forceinline__ LtTile lt_tile(long long t, int n_mt, long long n_nt, int group) {
     const long long per_group = (long long)group * n_mt;
     const long long g = t / per_group;
@@ -168,7 +190,7 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
                      const float *__restrict__ bias, const float *__restrict__ hdr, float *__restrict__ out,
                      int M, long long N, int nkb, int n_mt, long long n_nt, long long n_tiles,
                      unsigned long long *__restrict__ keys, unsigned *__restrict__ ticket,
-                     long long *__restrict__ argmax, float *__restrict__ maxval, int dbg, const LtLoss ls)
+                     long long *__restrict__ argmax, float *__restrict__ maxval, int dbg, const LtLoss ls, const int per_m)
 {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = lt_smem_u32(smem_raw);
@@ -181,8 +203,13 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
     const uint32_t bar_ofull = bars, bar_oempty = bars + 16, bar_tfull = bars + 32, bar_tempty = bars + 64;
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(smem + lt2::SMEM_BAR_OFF + 96);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long t_lo = n_tiles * blockIdx.x / gridDim.x, t_hi = n_tiles * (blockIdx.x + 1) / gridDim.x;
-    const int my_tiles = (int)(t_hi - t_lo);
+    const LtRange rg = lt_range(n_tiles, n_mt, n_nt, per_m);
+    const long long t_lo = rg.t_lo;
+    const int my_tiles = rg.my_tiles;
+    auto tile_of = [&](int i) {
+        if (rg.mt >= 0) { LtTile r; r.nt = t_lo + i; r.mt = rg.mt; return r; }
+        return lt_tile(t_lo + i, n_mt, n_nt, lt2::NT_GROUP);
+    };
     const bool want_arg = keys != nullptr;
 
     if (tid == 0) {
@@ -213,7 +240,7 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
         if (lane == 0) {
             int it = 0;
             for (int i = 0; i < my_tiles; ++i) {
-                const LtTile tt = lt_tile(t_lo + i, n_mt, n_nt, lt2::NT_GROUP);
+                const LtTile tt = tile_of(i);
                 const long long nt = tt.nt; const int mt = tt.mt;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int st = it & 1;
@@ -275,7 +302,7 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
         float *stg = stage_all + warp * 32 * lt2::STG_LD;
         float *sbias = reinterpret_cast<float *>(smem + lt2::SMEM_BIAS_OFF) + warp * 32;
         for (int i = 0; i < my_tiles; ++i) {
-            const LtTile tt = lt_tile(t_lo + i, n_mt, n_nt, lt2::NT_GROUP);
+            const LtTile tt = tile_of(i);
             const long long nt = tt.nt; const int mt = tt.mt;
             const int acc = i & (lt2::ACC_STAGES - 1);
             const long long col0 = nt * lt::TN + cq * 32;              // first column of this warp's block
@@ -629,11 +656,18 @@ int launch_label_tcgen05_ex(const c2v_dims *d, const float *cv, int B, const flo
     C2V_CUDA_OK(cudaFuncSetAttribute(label_gemm_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lt2::SMEM_BYTES));
     const long long n_tiles = (long long)mt * (long long)nt;
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    // tile order (see lt_range): lanes when that keeps >= 95 % of the CTAs busy, else groups; C2V_LABEL_ORDER=groups|lanes forces one
+    int per_m = (mt <= (size_t)grid) ? grid / (int)mt : 0;
+    if (per_m > 0 && (long long)per_m * (long long)mt * 100 < 95ll * grid) per_m = 0;
+    if (const char *ord = getenv("C2V_LABEL_ORDER")) {
+        if (!strcmp(ord, "groups")) per_m = 0;
+        else if (!strcmp(ord, "lanes") && mt <= (size_t)grid) per_m = grid / (int)mt;
+    }
     C2V_CUDA_OK(launch_pdl(label_gemm_v2_kernel, dim3((unsigned)grid), dim3(lt2::THREADS), (size_t)lt2::SMEM_BYTES, st,
                            (const uint8_t *)imgA, (const uint8_t *)imgB, bias, (const float *)hdr, out, B, C, nkb, (int)mt,
                            (long long)nt, n_tiles, fused_arg ? keys : (unsigned long long *)nullptr, ticket,
                            fused_arg ? argmax : (long long *)nullptr, fused_arg ? maxval : (float *)nullptr,
-                           getenv("C2V_K2_FLAGS") ? atoi(getenv("C2V_K2_FLAGS")) : 0, ls));
+                           getenv("C2V_K2_FLAGS") ? atoi(getenv("C2V_K2_FLAGS")) : 0, ls, per_m));
     C2V_LAUNCH_OK("label_gemm_v2_kernel");
     if (want_loss) {
         loss_partials_reduce_kernel<<<dim3((unsigned)(Mpad / 32), LT_PSPLIT), 256, 0, st>>>(part, (int)(nt * 4), Mpad, part2);
