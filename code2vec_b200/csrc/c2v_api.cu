@@ -48,7 +48,8 @@ bool label_backward_tc_ok(const c2v_dims *d);
 int label_w_image(const c2v_dims *d, const float *Wout, int B, void *ws, size_t ws_bytes, bool reuse_prep, cudaStream_t st,
                   const uint8_t **img, const float **hdr, unsigned **scratch);
 int launch_label_backward_tc(const c2v_dims *d, const float *cv, const float *G, int B, const uint8_t *w_img,
-                             const float *w_hdr, float *d_cv, float *d_w, float *d_b, unsigned *scratch, cudaStream_t st);
+                             const float *w_hdr, float *d_cv, float *d_w, float *d_b, unsigned *scratch, cudaStream_t st,
+                             bool absmax_ready);
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B);
 
 // ---- profiling hook (c2v_profile_enable / c2v_profile_read) ----------------------------
@@ -529,7 +530,7 @@ int c2v_label_backward_ws(const c2v_dims *d, const c2v_params *p, const float *c
                            &scratch);
     if (rc != C2V_OK) return rc;
     return launch_label_backward_tc(d, code_vector, d_outputs, B, img, hdr, d_code_vector, d_output_weight, d_output_bias,
-                                    scratch, st);
+                                    scratch, st, (algo & C2V_FLAG_GRAD_ABSMAX_READY) != 0);
 }
 
 size_t c2v_encode_backward_workspace_bytes(const c2v_dims *d, int32_t B, int32_t L)

@@ -307,7 +307,9 @@ backward_rows_lite_kernel(const EncodeArgs a, const BackwardArgs b)
 {
     constexpr int MAXC = 4 * NG;
     __shared__ float red[3 * 8 * 32 * MAXC];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp index through a lane-0 broadcast, so that the compiler sees the row loop and its branches as warp-uniform
+    // (otherwise every shuffle of the six warp sums per row is wrapped in WARPSYNC.COLLECTIVE / ENDCOLLECTIVE)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int H = a.H, L = a.L;
     const float invH = 1.0f / (float)H;
     float4 g4[NG], b4[NG], at4[NG];
@@ -331,7 +333,7 @@ backward_rows_lite_kernel(const EncodeArgs a, const BackwardArgs b)
     for (long long row = (long long)blockIdx.x * 8 + warp; row < a.N; row += n_warps) {
         const float alpha = b.att[row];
         float4 *dxr = reinterpret_cast<float4 *>(b.dx + row * H);
-        if (alpha == 0.0f) {                                   // padded context of a bag with valid ones: dx == 0
+        if (__all_sync(0xffffffffu, alpha == 0.0f)) {                                   // padded context of a bag with valid ones: dx == 0
 #pragma unroll
             for (int g = 0; g < NG; ++g) if (on[g]) dxr[g * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
             continue;

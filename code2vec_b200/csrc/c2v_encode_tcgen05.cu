@@ -79,23 +79,32 @@ bool tcgen05_shape_ok(const c2v_dims *d)
 // ------------------------------------------------------------------------------------
 // weight preparation: W [H, 3E] fp32 -> 3*NQ k-block images {hi tile, lo tile} of [HP n x 64 k] fp16 in the exact
 // shared-memory layout (K-major SWIZZLE_128B), scaled by 2^k; EP = HP = 128 (NQ = 2) or 256 (NQ = 4).  Sub-vector sv
-// (start / path / end) owns k-blocks NQ*sv .. NQ*sv + NQ-1; k >= E and n >= H are zero padding.  One CTA.
+// (start / path / end) owns k-blocks NQ*sv .. NQ*sv + NQ-1; k >= E and n >= H are zero padding.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__restrict__ hdr, int E, int H, int EP, int HP)
 {
+    // Several CTAs (the image is rebuilt every training step: one CTA took 22 us at 128/128/128 and 87 us at 256/256/256).
+    // Every CTA finds max |W| over the whole matrix itself (<= 768 KB, L2 hits after the first CTA): no second launch, no
+    // atomics, no pre-zeroed word.  Then one item = 4 consecutive k of one row n of the PADDED [HP][3 EP] matrix (zeros
+    // beyond E / H), i.e. 8 contiguous bytes of the hi tile and of the lo tile: every byte of the image is written once.
     __shared__ float red[32];
     const int tid = threadIdx.x;
     const int D = 3 * E, NQ = EP / tc::KB;
     const int tile_bytes = HP * tc::KB * 2, kb_bytes = 2 * tile_bytes;
+    const bool vec = (reinterpret_cast<uintptr_t>(W) & 15) == 0;       // E % 4 == 0 on this path: rows are 16-B multiples
     float mx = 0.0f;
-    for (int i = tid; i < H * D; i += 1024) mx = fmaxf(mx, fabsf(W[i]));
+    if (vec) {
+        const float4 *W4 = reinterpret_cast<const float4 *>(W);
+        for (int i = tid; i < H * D / 4; i += 1024) {
+            const float4 v = W4[i];
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+    } else {
+        for (int i = tid; i < H * D; i += 1024) mx = fmaxf(mx, fabsf(W[i]));
+    }
     mx = warp_max(mx);
     if ((tid & 31) == 0) red[tid >> 5] = mx;
-    if (E < EP || H < HP) {                                  // zero padding of the image
-        uint4 *z = reinterpret_cast<uint4 *>(img);
-        for (int i = tid; i < 3 * NQ * kb_bytes / 16; i += 1024) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
     __syncthreads();
     mx = red[0];
     for (int i = 1; i < 32; ++i) mx = fmaxf(mx, red[i]);
@@ -108,25 +117,31 @@ split_w_kernel(const float *__restrict__ W, uint8_t *__restrict__ img, float *__
         k = k > 60 ? 60 : (k < -60 ? -60 : k);
         scale = ldexpf(1.0f, k);
     }
-    if (tid == 0) { hdr[0] = 1.0f / scale; hdr[1] = scale; }
-    for (int i = tid; i < H * D; i += 1024) {
-        const int n = i / D, k = i % D;
-        const int sv = k / E, e = k % E;
-        const float w = W[i] * scale;
-        const __half hi = __float2half_rn(w);
-        const __half lo = __float2half_rn(w - __half2float(hi));
+    if (blockIdx.x == 0 && tid == 0) { hdr[0] = 1.0f / scale; hdr[1] = scale; }
+    const int per_row = 3 * EP / 4;
+    for (int g = blockIdx.x * 1024 + tid; g < HP * per_row; g += gridDim.x * 1024) {
+        const int n = g / per_row, kp = (g % per_row) * 4;
+        const int sv = kp / EP, e = kp % EP;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < H && e < E) {
+            const float *src = W + (size_t)n * D + sv * E + e;
+            w = vec ? *reinterpret_cast<const float4 *>(src) : make_float4(src[0], src[1], src[2], src[3]);
+        }
+        w.x *= scale; w.y *= scale; w.z *= scale; w.w *= scale;
+        const __half2 h01 = __floats2half2_rn(w.x, w.y), h23 = __floats2half2_rn(w.z, w.w);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(w.x - f01.x, w.y - f01.y), l23 = __floats2half2_rn(w.z - f23.x, w.w - f23.y);
         const int kb = NQ * sv + e / tc::KB, kk = e % tc::KB;
-        uint8_t *base = img + (size_t)kb * kb_bytes;
-        const uint32_t off = sw128_offset(n, kk);
-        *reinterpret_cast<__half *>(base + off) = hi;
-        *reinterpret_cast<__half *>(base + tile_bytes + off) = lo;
+        uint8_t *dst = img + (size_t)kb * kb_bytes + sw128_offset(n, kk);
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(pack_h2(h01), pack_h2(h23));
+        *reinterpret_cast<uint2 *>(dst + tile_bytes) = make_uint2(pack_h2(l01), pack_h2(l23));
     }
 }
 
 int launch_split_w_tcgen05(const c2v_dims *d, const float *W, EncodeWorkspace &ws, cudaStream_t st)
 {
     const int P = tm_wide(d->terminal_embed, d->encode) ? 256 : 128;
-    split_w_kernel<<<1, 1024, 0, st>>>(W, reinterpret_cast<uint8_t *>(ws.w_hi), ws.prep_hdr, d->terminal_embed, d->encode, P, P);
+    split_w_kernel<<<P == 256 ? 24 : 12, 1024, 0, st>>>(W, reinterpret_cast<uint8_t *>(ws.w_hi), ws.prep_hdr, d->terminal_embed, d->encode, P, P);
     C2V_LAUNCH_OK("split_w_kernel");
     return C2V_OK;
 }

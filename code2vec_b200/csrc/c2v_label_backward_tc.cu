@@ -490,16 +490,19 @@ bool label_backward_tc_ok(const c2v_dims *d)
 
 // scratch: 256 B (word 0: bits of max |G|).  w_img / w_hdr: the label workspace's cached W_out image and header (valid).
 int launch_label_backward_tc(const c2v_dims *d, const float *cv, const float *G, int B, const uint8_t *w_img,
-                             const float *w_hdr, float *d_cv, float *d_w, float *d_b, unsigned *scratch, cudaStream_t st)
+                             const float *w_hdr, float *d_cv, float *d_w, float *d_b, unsigned *scratch, cudaStream_t st,
+                             bool absmax_ready)
 {
     const int H = d->encode, nkb = (H + 63) / 64;
     const long long C = d->label_count;
     int dev = 0, sms = 0;
     C2V_CUDA_OK(cudaGetDevice(&dev));
     C2V_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    C2V_CUDA_OK(cudaMemsetAsync(scratch, 0, 4, st));
-    lbt_absmax_kernel<<<sms * 4, 256, 0, st>>>(G, (long long)B * C, scratch);
-    C2V_LAUNCH_OK("lbt_absmax_kernel");
+    if (!absmax_ready) {                       // (ready: c2v_label_dlogits left max |G| in the word while it wrote G)
+        C2V_CUDA_OK(cudaMemsetAsync(scratch, 0, 4, st));
+        lbt_absmax_kernel<<<sms * 4, 256, 0, st>>>(G, (long long)B * C, scratch);
+        C2V_LAUNCH_OK("lbt_absmax_kernel");
+    }
     if (d_w || d_b) {
         if (!d_w) { set_error("label backward (tensor cores): d_output_bias needs d_output_weight"); return C2V_EINVAL; }
         C2V_CUDA_OK(cudaFuncSetAttribute(label_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lb1::SMEM_BYTES));

@@ -151,6 +151,7 @@ __device__ __forceinline__ LtTile lt_tile(long long t, int n_mt, long long n_nt,
 //                  instead of the logit (main.py:174 through log_softmax + NLLLoss, weights == 1).
 struct LtLoss {
     float2 *part; float *tgt; const long long *label; const float *lse; const float *dscale_ptr; float dscale; int Mpad;
+    unsigned *gmax_bits;      // dlogits mode: bits of max |value stored| over the launch (what the label backward's fp16 split scales by)
 };
 constexpr float LT_LOG2E = 1.4426950408889634f;
 __device__ __forceinline__ float lt_ex2(float x) {
@@ -301,6 +302,7 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
         const bool vec_ok = (N % 4 == 0);
         float *stg = stage_all + warp * 32 * lt2::STG_LD;
         float *sbias = reinterpret_cast<float *>(smem + lt2::SMEM_BIAS_OFF) + warp * 32;
+        float gmax = 0.0f;                                    // dlogits mode: running max |d logit| of this thread
         for (int i = 0; i < my_tiles; ++i) {
             const LtTile tt = tile_of(i);
             const long long nt = tt.nt; const int mt = tt.mt;
@@ -359,6 +361,10 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
                     const float sc = ls.dscale_ptr ? ls.dscale * *ls.dscale_ptr : ls.dscale;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = (lt_ex2(fmaf(v[j], LT_LOG2E, -lb)) - ((j == (int)tj) ? 1.0f : 0.0f)) * sc;
+                    if (ls.gmax_bits && grow < M) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) gmax = fmaxf(gmax, j < n_cols ? fabsf(v[j]) : 0.0f);
+                    }
                 }
             }
             if (want_arg && lane < n_rows && n_cols > 0 && !C2V_EXPT(dbg, 2)) {
@@ -443,6 +449,10 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
                 }
             }
             __syncwarp();                         // staging tile is rewritten by the next tile
+        }
+        if (ls.lse && ls.gmax_bits) {                 // one atomic per warp and launch (non-negative floats order as uints)
+            gmax = warp_max(gmax);
+            if (lane == 0 && gmax > 0.0f && gmax < 3.0e38f) atomicMax(ls.gmax_bits, __float_as_uint(gmax));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -633,6 +643,10 @@ int launch_label_tcgen05_ex(const c2v_dims *d, const float *cv, int B, const flo
     if (la && la->dlogits_lse) {
         if (!la->label || !out) { set_error("label dlogits: label / output is NULL"); return C2V_EINVAL; }
         ls.lse = la->dlogits_lse; ls.label = la->label; ls.dscale = la->dscale; ls.dscale_ptr = la->dscale_ptr;
+        // max |d logit| for the label backward (c2v_label_backward_ws with C2V_FLAG_GRAD_ABSMAX_READY skips its own pass
+        // over the [B, C] gradient: 220 us at C = 195,299); same word label_w_image hands to the backward as `scratch`
+        ls.gmax_bits = reinterpret_cast<unsigned *>(p + 768);
+        C2V_CUDA_OK(cudaMemsetAsync(ls.gmax_bits, 0, 4, st));
     }
     const bool want_arg = argmax || maxval;
     const bool fused_arg = want_arg && mt <= (size_t)lt2::MAX_MT;

@@ -69,6 +69,7 @@ def make_params(emb_t, emb_p, W, ln_g, ln_b, attn, w_out=None, b_out=None):
 
 REUSE_PREP = 0x100
 NO_PDL = 0x200
+GRAD_ABSMAX_READY = 0x400
 
 
 class PrepCache:
@@ -325,9 +326,10 @@ def loss_argmax(outputs, label=None, want_grad=False):
 
 
 def label_backward(dims, params, cv, d_out, need_cv=True, need_w=True, need_b=True, algo=_lib.ALGO_AUTO, cache=None,
-                   weight=None):
+                   weight=None, absmax_ready=False):
     """backward of model.py:83 -> (d_code_vector, d_output_weight, d_output_bias).  With the label PrepCache of the
-    forward (cache + weight) the two contractions run on the tensor cores and stream the cached W_out image."""
+    forward (cache + weight) the two contractions run on the tensor cores and stream the cached W_out image.
+    absmax_ready: d_out is the tensor label_dlogits just returned for the same cache (skips the max |d_out| pass)."""
     lib = _lib.load()
     B = cv.shape[0]
     dev = cv.device
@@ -339,7 +341,7 @@ def label_backward(dims, params, cv, d_out, need_cv=True, need_w=True, need_b=Tr
         if cache is not None and weight is not None:
             nbytes = lib.c2v_label_workspace_bytes(ctypes.byref(dims), B)
             ws, reuse = cache.get(nbytes, dev, weight)
-            flags = int(algo) | (REUSE_PREP if reuse else 0)
+            flags = int(algo) | (REUSE_PREP if reuse else 0) | (GRAD_ABSMAX_READY if absmax_ready else 0)
             rc = lib.c2v_label_backward_ws(ctypes.byref(dims), ctypes.byref(params), _ptr(cv), _ptr(d_out), B, _ptr(d_cv),
                                            _ptr(d_w), _ptr(d_b), _ptr(ws), ws.numel(), flags, _stream(dev))
             _lib.check(rc, "c2v_label_backward_ws")

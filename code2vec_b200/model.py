@@ -150,7 +150,8 @@ class _LabelLossFn(torch.autograd.Function):
         d_out = CF.label_dlogits(ctx.dims, params, cv, label, lse, 1.0 / B, scale_device=d_loss.reshape(1),
                                  algo=ctx.algo, cache=ctx.cache, weight=w_out)
         d_cv, d_w, d_b = CF.label_backward(ctx.dims, params, cv, d_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                           ctx.needs_input_grad[2], algo=int(ctx.algo) & 0xff, cache=ctx.cache, weight=w_out)
+                                           ctx.needs_input_grad[2], algo=int(ctx.algo) & 0xff, cache=ctx.cache, weight=w_out,
+                                           absmax_ready=True)
         return d_cv, d_w, d_b, None, None, None, None
 
 

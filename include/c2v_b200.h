@@ -65,6 +65,10 @@ enum {
  * launches (the default overlaps each kernel's prologue with its predecessor's tail).  The training forward
  * (c2v_encode_forward_stash with a stash) always does. */
 #define C2V_FLAG_NO_PDL 0x200
+/* OR-ed into `algo` of c2v_label_backward_ws: `d_outputs` is what c2v_label_dlogits wrote with this same workspace (and no
+ * other call has used the workspace since), so max |d_outputs| -- the scale of the fp16 split -- is already in the
+ * workspace and the pass over the [B, C] gradient that finds it is skipped.  Results are bit-identical either way. */
+#define C2V_FLAG_GRAD_ABSMAX_READY 0x400
 
 /* Sizes read from the reference's Option (main.py:93-115) by Code2Vec.__init__
  * (model.py:18-42). */
@@ -219,7 +223,8 @@ int c2v_label_backward(const c2v_dims *d, const c2v_params *p, const float *code
                        float *d_output_weight, float *d_output_bias, void *stream);
 /* c2v_label_backward on the tensor cores (dW_out = d_out^T . cv with the column sums d_b folded in, d_cv = d_out . W_out
  * streaming the cached W_out image): `workspace` is the label workspace of c2v_label_logits* for this weight
- * (C2V_FLAG_REUSE_PREP in `algo` = its image is current, e.g. the forward of the same step built it).  Falls back to
+ * (C2V_FLAG_REUSE_PREP in `algo` = its image is current, e.g. the forward of the same step built it;
+ * C2V_FLAG_GRAD_ABSMAX_READY = d_outputs comes from c2v_label_dlogits on this workspace).  Falls back to
  * c2v_label_backward (CUDA cores) when workspace == NULL, encode_size % 4 != 0 or > 256, or algo == C2V_ALGO_FFMA. */
 int c2v_label_backward_ws(const c2v_dims *d, const c2v_params *p, const float *code_vector, const float *d_outputs,
                           int32_t B, float *d_code_vector, float *d_output_weight, float *d_output_bias, void *workspace,

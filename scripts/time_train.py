@@ -1,4 +1,4 @@
-"""launch-level breakdown of one training step (torch profiler, CUDA time per kernel)"""
+"""launch-level breakdown of one training step (torch profiler, CUDA time per kernel);  WORKLOAD=cfg2|cfg3|cfg4|cfg5"""
 import sys, os, types
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R)
@@ -7,11 +7,11 @@ from torch.profiler import profile, ProfilerActivity
 from bench import WORKLOADS, synth_params, synth_pool
 from code2vec_b200.model import Code2Vec
 from code2vec_b200.distributed import ShardedFlatAdam, ddp_step
-w = dict(WORKLOADS["cfg2"]); dev = torch.device("cuda:0")
+w = dict(WORKLOADS[os.environ.get("WORKLOAD", "cfg2")]); dev = torch.device("cuda:0")
 p = synth_params(w, dev); s, pth, e, lab = synth_pool(w, 8, dev, 1)
 B = w["B"]
-o = types.SimpleNamespace(terminal_count=w["T"], path_count=w["P"], label_count=w["C"], terminal_embed_size=128,
-                          path_embed_size=128, encode_size=128, dropout_prob=0.25, angular_margin_loss=False,
+o = types.SimpleNamespace(terminal_count=w["T"], path_count=w["P"], label_count=w["C"], terminal_embed_size=w["Et"],
+                          path_embed_size=w["Ep"], encode_size=w["H"], dropout_prob=0.25, angular_margin_loss=False,
                           angular_margin=0.5, inverse_temp=30.0, device=dev)
 m = Code2Vec(o); m.load_state_dict(p); m = m.to(dev).train()
 opt = ShardedFlatAdam(m.parameters(), lr=0.01); bucket = None

@@ -122,3 +122,26 @@ def test_label_backward_tensor_cores(B, C, H, gscale):
     # and the CUDA-core path gives the same answer (no workspace)
     d_cv2, d_w2, d_b2 = CF.label_backward(dims, params, cuda(cv), cuda(G))
     assert np.abs(d_cv2.cpu().numpy() - ref_dcv).max() <= 2e-5 * max(float(np.abs(ref_dcv).max()), 1e-30)
+
+
+@pytest.mark.parametrize("B,C,H", [(130, 1000, 128), (64, 4097, 100), (33, 260, 256), (1024, 8192, 128)])
+def test_dlogits_leaves_the_gradient_maximum_for_the_label_backward(B, C, H):
+    """c2v_label_dlogits keeps max |d logit| in the label workspace while it writes the gradient;
+    c2v_label_backward_ws(C2V_FLAG_GRAD_ABSMAX_READY) then skips its own pass over [B, C]: same result as without the
+    flag, and right against fp64 products of the same gradient."""
+    rng = np.random.default_rng(B * 3 + C)
+    cv, W, b, lab = _case(rng, B, C, H, 4.0)
+    dims = CF.make_dims(10, 10, C, H, H, H)
+    w_t = cuda(W)
+    params = CF.make_params(None, None, None, None, None, None, w_t, cuda(b))
+    cache = CF.PrepCache()
+    loss, lse, am, mx, out = CF.label_loss(dims, params, cuda(cv), cuda(lab), cache=cache, weight=w_t)
+    G = CF.label_dlogits(dims, params, cuda(cv), cuda(lab), lse, 1.0 / B, cache=cache, weight=w_t)
+    fast = CF.label_backward(dims, params, cuda(cv), G, cache=cache, weight=w_t, absmax_ready=True)
+    slow = CF.label_backward(dims, params, cuda(cv), G, cache=cache, weight=w_t)
+    # d_w / d_b: one CTA owns a label tile (deterministic) -> identical bits; d_cv is a split-K sum through atomics
+    assert torch.equal(fast[1], slow[1]) and torch.equal(fast[2], slow[2])
+    assert (fast[0] - slow[0]).abs().max().item() <= 1e-6 * slow[0].abs().max().item()
+    g64 = G.cpu().numpy().astype(np.float64)
+    for got, ref in ((fast[0], g64 @ W.astype(np.float64)), (fast[1], g64.T @ cv.astype(np.float64)), (fast[2], g64.sum(0))):
+        assert np.abs(got.cpu().numpy() - ref).max() <= 2e-5 * max(float(np.abs(ref).max()), 1e-30)
