@@ -264,7 +264,7 @@ def test_angular_head_gradients_match_reference_autograd(name):
         assert np.abs(p.grad.cpu().numpy() - ref).max() <= _tol(ref), k
 
 
-@pytest.mark.parametrize("name", ["grad_cfg2", "grad_cfg1", "grad_odd"])
+@pytest.mark.parametrize("name", ["grad_cfg2", "grad_cfg1", "grad_odd", "grad_wide", "grad_e200"])
 def test_fused_grad_accumulation_equals_autograd_accumulation(name):
     """Code2Vec.fuse_grad_accumulation: the table / input_linear gradients are added straight into existing .grad buffers
     (what ddp_step uses with the flat optimizers) -- same result as letting autograd accumulate fresh gradient tensors."""
