@@ -46,10 +46,10 @@ size_t encode_backward_workspace_bytes(const c2v_dims *d, int B, int L);
 bool label_tcgen05_shape_ok(const c2v_dims *d);
 bool label_backward_tc_ok(const c2v_dims *d);
 int label_w_image(const c2v_dims *d, const float *Wout, int B, void *ws, size_t ws_bytes, bool reuse_prep, cudaStream_t st,
-                  const uint8_t **img, const float **hdr, unsigned **scratch);
+                  const uint8_t **img, const float **hdr, unsigned **scratch, const uint8_t **cv_img);
 int launch_label_backward_tc(const c2v_dims *d, const float *cv, const float *G, int B, const uint8_t *w_img,
                              const float *w_hdr, float *d_cv, float *d_w, float *d_b, unsigned *scratch, cudaStream_t st,
-                             bool absmax_ready);
+                             bool absmax_ready, const uint8_t *cv_img);
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B);
 
 // ---- profiling hook (c2v_profile_enable / c2v_profile_read) ----------------------------
@@ -525,12 +525,15 @@ int c2v_label_backward_ws(const c2v_dims *d, const c2v_params *p, const float *c
         return c2v_label_backward(d, p, code_vector, d_outputs, B, d_code_vector, d_output_weight, d_output_bias, stream);
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const uint8_t *img = nullptr; const float *hdr = nullptr; unsigned *scratch = nullptr;
+    const uint8_t *img = nullptr, *cv_img = nullptr; const float *hdr = nullptr; unsigned *scratch = nullptr;
     int rc = label_w_image(d, p->output_weight, B, workspace, workspace_bytes, (algo & C2V_FLAG_REUSE_PREP) != 0, st, &img, &hdr,
-                           &scratch);
+                           &scratch, &cv_img);
     if (rc != C2V_OK) return rc;
+    // after c2v_label_dlogits on this workspace (the flag's contract: same code_vector, nothing in between) the workspace also
+    // holds max |d_outputs| and the fp16 image of code_vector: the backward reads both instead of recomputing them
+    const bool from_dlogits = (algo & C2V_FLAG_GRAD_ABSMAX_READY) != 0;
     return launch_label_backward_tc(d, code_vector, d_outputs, B, img, hdr, d_code_vector, d_output_weight, d_output_bias,
-                                    scratch, st, (algo & C2V_FLAG_GRAD_ABSMAX_READY) != 0);
+                                    scratch, st, from_dlogits, from_dlogits ? cv_img : nullptr);
 }
 
 size_t c2v_encode_backward_workspace_bytes(const c2v_dims *d, int32_t B, int32_t L)

@@ -81,9 +81,17 @@ constexpr int SMEM_BYTES = SMEM_BAR_OFF + 128 + 1024;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }  // namespace lb1
 
+// CV_IMG: the B operand (cv) is not converted here at all: `cv_img` is the fp16 hi/lo image of cv that the label GEMM of the
+// same step left in the label workspace ([128 bags x 64 h] K-major SWIZZLE_128B tiles = the very bytes an MN-major B tile
+// of this GEMM needs), streamed by warp 21 with one 32 KB cp.async.bulk per (batch tile, k-block); the producers then only
+// handle G and issue a step's whole G tile (8 pieces per lane) before they wait for the stage.  Per (label tile, batch tile)
+// step the producers' chain was four dependent load -> convert -> store rounds (~5-7 us: 623 us for the 1,526 label tiles
+// of top11); now one.
+template <bool CV_IMG>
 __global__ void __launch_bounds__(lbt::THREADS, 1)
 label_dw_tc_kernel(const float *__restrict__ G, const float *__restrict__ cv, int B, long long C, int H, int nkb,
-                   const unsigned *__restrict__ g_absmax, float *__restrict__ dW, float *__restrict__ d_bias)
+                   const unsigned *__restrict__ g_absmax, float *__restrict__ dW, float *__restrict__ d_bias,
+                   const uint8_t *__restrict__ cv_img)
 {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -107,7 +115,7 @@ label_dw_tc_kernel(const float *__restrict__ G, const float *__restrict__ cv, in
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_afull + 8 * s, 2 * lbt::N_PROD_WARPS);
             mbar_init(bar_aempty + 8 * s, 1);
-            mbar_init(bar_bfull + 8 * s, lbt::N_PROD_WARPS);
+            mbar_init(bar_bfull + 8 * s, CV_IMG ? 1 : lbt::N_PROD_WARPS);
             mbar_init(bar_bempty + 8 * s, 1);
             mbar_init(bar_accfull + 8 * s, 1);
             mbar_init(bar_accempty + 8 * s, 4);
@@ -144,6 +152,18 @@ label_dw_tc_kernel(const float *__restrict__ G, const float *__restrict__ cv, in
             for (int bt = 0; bt < n_bt; ++bt, ++ita) {
                 const int row0 = bt * 128 + pw * lbt::ROWS_PER_PW;
                 const int as = ita & 1;
+                float4 g[2][4];
+                if (CV_IMG) {                            // the step's whole G tile in flight before the stage wait
+#pragma unroll
+                    for (int p = 0; p < 2; ++p)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int r = row0 + 2 * j + sub_row;
+                            const long long c = c0 + p * 64 + q * 4;
+                            g[p][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (r < B) g[p][j] = lbt_load4(G + (size_t)r * C + c, C - c, vecG);
+                        }
+                }
                 mbar_wait(bar_aempty + 8 * as, (((uint32_t)(ita >> 1)) & 1u) ^ 1u, status);
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
@@ -153,7 +173,8 @@ label_dw_tc_kernel(const float *__restrict__ G, const float *__restrict__ cv, in
                         const int r = row0 + 2 * j + sub_row;
                         const long long c = c0 + p * 64 + q * 4;
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r < B) v = lbt_load4(G + (size_t)r * C + c, C - c, vecG);
+                        if (CV_IMG) v = g[p][j];
+                        else if (r < B) v = lbt_load4(G + (size_t)r * C + c, C - c, vecG);
                         cs[p].x += v.x; cs[p].y += v.y; cs[p].z += v.z; cs[p].w += v.w;
                         v.x *= g_scale; v.y *= g_scale; v.z *= g_scale; v.w *= g_scale;
                         lbt_split_store(hi, lo, st_off[j], v);
@@ -163,7 +184,7 @@ label_dw_tc_kernel(const float *__restrict__ G, const float *__restrict__ cv, in
                     if (lane == 0) mbar_arrive(bar_afull + 8 * as);
                 }
 #pragma unroll 1
-                for (int kb = 0; kb < nkb; ++kb, ++itb) {
+                for (int kb = 0; kb < (CV_IMG ? 0 : nkb); ++kb, ++itb) {
                     const int bs = itb & 1;
                     float4 buf[4];
 #pragma unroll
@@ -201,6 +222,21 @@ label_dw_tc_kernel(const float *__restrict__ G, const float *__restrict__ cv, in
                 named_bar_sync(2, lbt::N_PROD_WARPS * 32);                // scratch is rewritten by the next label tile
             }
         }
+    } else if (CV_IMG && warp == lbt::BULK_WARP) {
+        // =============================== cv IMAGE PRODUCER (cp.async.bulk) ===============================
+        if (lane == 0) {
+            int itb = 0;
+            for (int cl = 0; cl < my_ct; ++cl)
+                for (int bt = 0; bt < n_bt; ++bt)
+                    for (int kb = 0; kb < nkb; ++kb, ++itb) {
+                        const int bs = itb & 1;
+                        mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(itb >> 1)) & 1u) ^ 1u, status);
+                        mbar_arrive_expect_tx(bar_bfull + 8 * bs, lb1::B_SLOT);
+                        bulk_copy_g2s(base + lb1::SMEM_B_OFF + bs * lb1::B_SLOT, cv_img + ((size_t)bt * nkb + kb) * lb1::B_SLOT,
+                                      lb1::B_SLOT, bar_bfull + 8 * bs);
+                    }
+        }
+        __syncwarp();
     } else if (warp == lbt::MMA_WARP) {
         // =============================== MMA ISSUER (converged, one elected lane) ===============================
         int ita = 0, itb = 0;
@@ -491,7 +527,7 @@ bool label_backward_tc_ok(const c2v_dims *d)
 // scratch: 256 B (word 0: bits of max |G|).  w_img / w_hdr: the label workspace's cached W_out image and header (valid).
 int launch_label_backward_tc(const c2v_dims *d, const float *cv, const float *G, int B, const uint8_t *w_img,
                              const float *w_hdr, float *d_cv, float *d_w, float *d_b, unsigned *scratch, cudaStream_t st,
-                             bool absmax_ready)
+                             bool absmax_ready, const uint8_t *cv_img)
 {
     const int H = d->encode, nkb = (H + 63) / 64;
     const long long C = d->label_count;
@@ -505,10 +541,11 @@ int launch_label_backward_tc(const c2v_dims *d, const float *cv, const float *G,
     }
     if (d_w || d_b) {
         if (!d_w) { set_error("label backward (tensor cores): d_output_bias needs d_output_weight"); return C2V_EINVAL; }
-        C2V_CUDA_OK(cudaFuncSetAttribute(label_dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lb1::SMEM_BYTES));
+        auto kern = cv_img ? label_dw_tc_kernel<true> : label_dw_tc_kernel<false>;
+        C2V_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lb1::SMEM_BYTES));
         const long long n_ct = (C + 127) / 128;
         const int grid = (int)(n_ct < sms ? n_ct : sms);
-        label_dw_tc_kernel<<<grid, lbt::THREADS, lb1::SMEM_BYTES, st>>>(G, cv, B, C, H, nkb, scratch, d_w, d_b);
+        kern<<<grid, lbt::THREADS, lb1::SMEM_BYTES, st>>>(G, cv, B, C, H, nkb, scratch, d_w, d_b, cv_img);
         C2V_LAUNCH_OK("label_dw_tc_kernel");
     }
     if (d_cv) {

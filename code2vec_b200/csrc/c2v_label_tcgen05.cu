@@ -565,7 +565,7 @@ int launch_label_tcgen05_ex(const c2v_dims *d, const float *cv, int B, const flo
 
 // The cached W_out image of a label workspace (built here unless reuse_prep): what the tensor-core label backward streams.
 int label_w_image(const c2v_dims *d, const float *Wout, int B, void *ws, size_t ws_bytes, bool reuse_prep, cudaStream_t st,
-                  const uint8_t **img, const float **hdr, unsigned **scratch)
+                  const uint8_t **img, const float **hdr, unsigned **scratch, const uint8_t **cv_img)
 {
     if (!label_tcgen05_shape_ok(d) || !ws || ws_bytes < label_tcgen05_workspace_bytes(d, B)) {
         set_error("label backward: workspace missing or too small");
@@ -588,6 +588,8 @@ int label_w_image(const c2v_dims *d, const float *Wout, int B, void *ws, size_t 
         C2V_LAUNCH_OK("split_rows_kernel");
     }
     *img = imgB; *hdr = h; *scratch = reinterpret_cast<unsigned *>(p + 768);
+    // where launch_label_tcgen05_ex keeps the fp16 image of the code vectors of its last call with this B (same layout math)
+    if (cv_img) *cv_img = imgB + (size_t)((C + 127) / 128) * nkb * 2 * lt::TILE_BYTES + lt_keys_bytes(B);
     return C2V_OK;
 }
 

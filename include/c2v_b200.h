@@ -65,9 +65,10 @@ enum {
  * launches (the default overlaps each kernel's prologue with its predecessor's tail).  The training forward
  * (c2v_encode_forward_stash with a stash) always does. */
 #define C2V_FLAG_NO_PDL 0x200
-/* OR-ed into `algo` of c2v_label_backward_ws: `d_outputs` is what c2v_label_dlogits wrote with this same workspace (and no
- * other call has used the workspace since), so max |d_outputs| -- the scale of the fp16 split -- is already in the
- * workspace and the pass over the [B, C] gradient that finds it is skipped.  Results are bit-identical either way. */
+/* OR-ed into `algo` of c2v_label_backward_ws: `d_outputs` is what c2v_label_dlogits wrote with this same workspace for
+ * this same `code_vector` and B (and no other call has used the workspace since).  The workspace then already holds
+ * max |d_outputs| -- the scale of the fp16 split -- and the fp16 image of code_vector, so the pass over the [B, C] gradient
+ * that finds the former and the per-tile conversion of the latter are skipped.  Same results either way. */
 #define C2V_FLAG_GRAD_ABSMAX_READY 0x400
 
 /* Sizes read from the reference's Option (main.py:93-115) by Code2Vec.__init__

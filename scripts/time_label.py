@@ -29,13 +29,16 @@ def run(kind, reuse=True):
     if kind == "loss pass over stored logits": return lib.c2v_loss_argmax(P(out), P(lab), B, C, P(loss), P(am), P(mx), None, st)
     if kind == "dlogits": return lib.c2v_label_dlogits(D, PR, P(cv), P(lab), P(lse), B, 1.0 / B, None, P(out), P(ws), n, a, st)
     if kind == "backward tensor cores": return lib.c2v_label_backward_ws(D, PR, P(cv), P(out), B, P(dcv), P(dw), P(db), P(ws), n, a, st)
+    if kind == "backward tensor cores after dlogits":      # C2V_FLAG_GRAD_ABSMAX_READY: max |G| and the cv image come from the workspace
+        return lib.c2v_label_backward_ws(D, PR, P(cv), P(out), B, P(dcv), P(dw), P(db), P(ws), n, a | 0x400, st)
     if kind == "backward cuda cores": return lib.c2v_label_backward(D, PR, P(cv), P(out), B, P(dcv), P(dw), P(db), st)
 assert run("logits", False) == 0; torch.cuda.synchronize()
 kinds = ["logits", "logits+argmax", "loss+argmax, no logits", "loss+argmax+logits", "loss pass over stored logits", "dlogits",
-         "backward tensor cores", "backward cuda cores"]
+         "backward tensor cores", "backward tensor cores after dlogits", "backward cuda cores"]
 for kind in kinds:
     if ONLY and ONLY not in kind: continue
     reps = 20 if C > 50000 else 50
+    if kind.endswith("after dlogits"): assert run("dlogits") == 0
     for _ in range(3): assert run(kind) == 0, lib.c2v_last_error()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
