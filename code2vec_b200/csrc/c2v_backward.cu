@@ -330,8 +330,15 @@ backward_rows_lite_kernel(const EncodeArgs a, const BackwardArgs b)
     for (int k = 0; k < MAXC; ++k) acc_a[k] = acc_g[k] = acc_b[k] = 0.0f;
     float dx_max = 0.0f;
     const long long n_warps = (long long)gridDim.x * 8;
-    for (long long row = (long long)blockIdx.x * 8 + warp; row < a.N; row += n_warps) {
-        const float alpha = b.att[row];
+    // the attention weight of the NEXT row is fetched one iteration ahead: alpha gates the row's other loads (padded rows
+    // skip them), so fetched in place it put two dependent memory latencies on every row (ncu: the top stalls were the
+    // first uses of these loads)
+    const long long row_first = (long long)blockIdx.x * 8 + warp;
+    float alpha_next = row_first < a.N ? b.att[row_first] : 0.0f;
+    for (long long row = row_first; row < a.N; row += n_warps) {
+        const float alpha = alpha_next;
+        alpha_next = row + n_warps < a.N ? b.att[row + n_warps] : 0.0f;
+        const long long start_idx = a.starts[row];              // (used late: issued here so that it overlaps the row loads)
         float4 *dxr = reinterpret_cast<float4 *>(b.dx + row * H);
         if (__all_sync(0xffffffffu, alpha == 0.0f)) {                                   // padded context of a bag with valid ones: dx == 0
 #pragma unroll
@@ -382,7 +389,7 @@ backward_rows_lite_kernel(const EncodeArgs a, const BackwardArgs b)
         float extra = 0.0f, sbag = 0.0f;
         if (b.d_att) { extra = b.d_att[row]; sbag = b.sb[bag]; }
         const float dz = alpha * (dal + extra - gvv - sbag);
-        const float du = a.starts[row] > 0 ? dz : 0.0f;          // mask = starts > 0 (model.py:64)
+        const float du = start_idx > 0 ? dz : 0.0f;              // mask = starts > 0 (model.py:64)
         float dxh[MAXC];
         float m1 = 0.0f, m2 = 0.0f;
 #pragma unroll

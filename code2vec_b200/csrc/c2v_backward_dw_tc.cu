@@ -14,7 +14,11 @@
 //
 // One persistent CTA per SM walks 128-row tiles and keeps its partial dW [128 h x 384 d] in TMEM (384 columns) for
 // the whole launch; at the end 4 warps add it to the global gradient with 128-bit vector atomics.
-// Warps: 0-3 final reduction | 4-19 producers (8 rows each: LDG.128 -> hi/lo split -> STS.64) | 20 MMA issuer.
+// Warps: 0-15 producers (8 rows each: LDG.128 -> hi/lo split -> STS.64; warps 0-3 also do the final reduction) | 16 MMA
+// issuer.  17 warps leave 96 registers per thread: a producer keeps TWO panels of loads in flight (both dX panels of a tile
+// before it waits for the stage; gathered panel kb+1 while it converts panel kb) -- with one panel at a time the eight
+// dependent load -> convert -> store rounds per tile were the whole kernel (ncu: 40 % of the stall samples on the first
+// use of a load, tensor pipe 26 %).
 // smem: 2 tile-stages of the dX operand {hi p0, hi p1, lo p0, lo p1} (128 KB) + 2 slots of one gathered panel {hi, lo}
 // (64 KB); per tile 6 gathered panels (start / path / end x 2 halves) stream through the slots: 144 MMAs (N = 64).
 // Windows: blockIdx.y = hb * n_db + db selects rows h in [128 hb, 128 hb + 128) of dW and, inside each of the three
@@ -31,8 +35,8 @@ constexpr int ROWS = 128, H = 128, E = 128, D = 3 * E;
 constexpr int PANEL = ROWS * 64 * 2;                  // 16 KB: [128 rows x 64 cols] fp16
 constexpr int A_STAGE = 4 * PANEL;                    // hi p0 | hi p1 | lo p0 | lo p1
 constexpr int B_SLOT = 2 * PANEL;                     // hi | lo
-constexpr int N_PROD_WARPS = 16, PROD_WARP0 = 4, MMA_WARP = 20;
-constexpr int THREADS = 21 * 32;
+constexpr int N_PROD_WARPS = 16, PROD_WARP0 = 0, MMA_WARP = 16;
+constexpr int THREADS = 17 * 32;
 constexpr int ROWS_PER_PW = ROWS / N_PROD_WARPS;      // 8
 constexpr int NB = 6;                                 // gathered panels per tile
 constexpr int SMEM_A_OFF = 0, SMEM_B_OFF = 2 * A_STAGE, SMEM_BAR_OFF = SMEM_B_OFF + 2 * B_SLOT;
@@ -133,51 +137,83 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
             const long long myrow = row0 + (lane & 7);
             long long is = 0, ip = 0, ie = 0;
             if (myrow < a.N) { is = a.starts[myrow]; ip = a.paths[myrow]; ie = a.ends[myrow]; }
+            // ---- dX operand: both panels (h 0..63, 64..127 of the window) in flight before the stage wait
+            float4 buf[2][4];
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long r = row0 + 2 * j + sub_row;
+                    buf[p][j] = (r < a.N && h04 + p * 16 + q < H4) ? ldg_nc_v4(dx4 + (size_t)r * H4 + h04 + p * 16 + q)
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             if (is < 0 || is >= a.T) is = 0;
             if (ip < 0 || ip >= a.P) ip = 0;
             if (ie < 0 || ie >= a.T) ie = 0;
             const uint32_t off_s = (uint32_t)(is * E4), off_p = (uint32_t)(ip * E4), off_e = (uint32_t)(ie * E4);
-            // ---- dX operand: two panels (h 0..63, 64..127) into tile-stage tl & 1
             const int as = tl & 1;
             mbar_wait(bar_aempty + 8 * as, (((uint32_t)(tl >> 1)) & 1u) ^ 1u, status);
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
-                float4 buf[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const long long r = row0 + 2 * j + sub_row;
-                    buf[j] = (r < a.N && h04 + p * 16 + q < H4) ? ldg_nc_v4(dx4 + (size_t)r * H4 + h04 + p * 16 + q)
-                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-                    buf[j].x *= dx_scale; buf[j].y *= dx_scale; buf[j].z *= dx_scale; buf[j].w *= dx_scale;
+                    buf[p][j].x *= dx_scale; buf[p][j].y *= dx_scale; buf[p][j].z *= dx_scale; buf[p][j].w *= dx_scale;
                 }
                 const uint32_t hi = base + dwt::SMEM_A_OFF + as * dwt::A_STAGE + p * dwt::PANEL;
-                split_store(hi, hi + 2 * dwt::PANEL, buf);
+                split_store(hi, hi + 2 * dwt::PANEL, buf[p]);
                 fence_proxy_async_smem();             // writer side: generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_afull + 8 * as);
             }
-            // ---- gathered operand: 6 panels through the 2-slot ring
-#pragma unroll 1
-            for (int kb = 0; kb < dwt::NB; ++kb, ++itb) {
+            // ---- gathered operand: 6 panels through the 2-slot ring, panel kb+1's loads in flight while kb is converted
+            auto gather = [&](float4 (&dst)[4], int kb) {
                 const int sv = kb >> 1;
                 const float4 *tab = sv == 1 ? tab_p : tab_t;
                 const uint32_t off = sv == 0 ? off_s : (sv == 1 ? off_p : off_e);
-                float4 buf[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t o = __shfl_sync(0xffffffffu, off, 2 * j + sub_row);
                     const long long r = row0 + 2 * j + sub_row;
-                    buf[j] = (r < a.N && d04 + (kb & 1) * 16 + q < E4) ? ldg_nc_v4(tab + (size_t)o + d04 + (kb & 1) * 16 + q)
+                    dst[j] = (r < a.N && d04 + (kb & 1) * 16 + q < E4) ? ldg_nc_v4(tab + (size_t)o + d04 + (kb & 1) * 16 + q)
                                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+            };
+            gather(buf[0], 0);
+#pragma unroll
+            for (int kb = 0; kb < dwt::NB; ++kb, ++itb) {
+                if (kb + 1 < dwt::NB) gather(buf[(kb + 1) & 1], kb + 1);
                 const int bs = itb & 1;
                 mbar_wait(bar_bempty + 8 * bs, (((uint32_t)(itb >> 1)) & 1u) ^ 1u, status);
                 const uint32_t hi = base + dwt::SMEM_B_OFF + bs * dwt::B_SLOT;
-                split_store(hi, hi + dwt::PANEL, buf);
+                split_store(hi, hi + dwt::PANEL, buf[kb & 1]);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_bfull + 8 * bs);
             }
+        }
+        if (warp < 4 && my_tiles > 0) {
+            // =============================== FINAL REDUCTION ===============================
+            // thread = row h of dW (TMEM lane); 384 accumulator columns = d; added to the global gradient with 128-bit atomics
+            mbar_wait(bar_acc, 0u, status);
+            tc_fence_after();
+            const int h = hb * 128 + warp * 32 + lane;
+            const float inv = 1.0f / dx_scale;
+            const int E = a.Et;
+            float *dst = dW + (size_t)h * (3 * E);                 // dW is [H][3E]; accumulator column sv * 128 + (d - 128 db)
+#pragma unroll 1
+            for (int c = 0; c < dwt::D / 32; ++c) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                const int sv = c >> 2, d0 = db * 128 + (c & 3) * 32;
+                if (h < a.H) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (d0 + j < E)
+                            red_add_v4(dst + sv * E + d0 + j, make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv));
+                }
+            }
+            tc_fence_before();
         }
     } else if (warp == dwt::MMA_WARP) {
         // =============================== MMA ISSUER (converged, one elected lane) ===============================
@@ -215,29 +251,6 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                 __syncwarp();
             }
         }
-    } else if (my_tiles > 0) {
-        // =============================== FINAL REDUCTION ===============================
-        // thread = row h of dW (TMEM lane); 384 accumulator columns = d; added to the global gradient with 128-bit atomics
-        mbar_wait(bar_acc, 0u, status);
-        tc_fence_after();
-        const int h = hb * 128 + warp * 32 + lane;
-        const float inv = 1.0f / dx_scale;
-        const int E = a.Et;
-        float *dst = dW + (size_t)h * (3 * E);                 // dW is [H][3E]; accumulator column sv * 128 + (d - 128 db)
-#pragma unroll 1
-        for (int c = 0; c < dwt::D / 32; ++c) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-            tmem_ld_wait();
-            const int sv = c >> 2, d0 = db * 128 + (c & 3) * 32;
-            if (h < a.H) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    if (d0 + j < E)
-                        red_add_v4(dst + sv * E + d0 + j, make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv));
-            }
-        }
-        tc_fence_before();
     }
     tc_fence_before();
     __syncthreads();

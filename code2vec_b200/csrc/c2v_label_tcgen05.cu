@@ -303,6 +303,15 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
         float *stg = stage_all + warp * 32 * lt2::STG_LD;
         float *sbias = reinterpret_cast<float *>(smem + lt2::SMEM_BIAS_OFF) + warp * 32;
         float gmax = 0.0f;                                    // dlogits mode: running max |d logit| of this thread
+        // bias of the NEXT tile's 32 columns is fetched one tile ahead (a dependent global load at the top of every tile
+        // otherwise sits on each warp's critical path: ~0.7 us of the ~4 us a tile takes)
+        auto bias_of = [&](int i) {
+            if (!bias || i >= my_tiles) return 0.0f;
+            const LtTile t2 = tile_of(i);
+            const long long c2 = t2.nt * lt::TN + cq * 32 + lane;
+            return c2 < N ? __ldg(bias + c2) : 0.0f;
+        };
+        float bias_next = bias_of(0);
         for (int i = 0; i < my_tiles; ++i) {
             const LtTile tt = tile_of(i);
             const long long nt = tt.nt; const int mt = tt.mt;
@@ -312,8 +321,9 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
             const int n_cols = (int)(N - col0 < 32 ? N - col0 : 32);   // valid columns / rows of the block (may be <= 0)
             const int n_rows = (int)(M - row0 < 32 ? M - row0 : 32);
             // bias of this warp's 32 columns: one element per lane -> smem -> broadcast float4 reads
-            sbias[lane] = (bias && lane < n_cols) ? __ldg(bias + col0 + lane) : 0.0f;
+            sbias[lane] = bias_next;
             __syncwarp();
+            bias_next = bias_of(i + 1);
             lt_mbar_wait(bar_tfull + 8 * acc, (uint32_t)(i / lt2::ACC_STAGES) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * lt::TN + cq * 32);
@@ -350,9 +360,15 @@ label_gemm_v2_kernel(const uint8_t *__restrict__ imgA, const uint8_t *__restrict
                     for (int j = 0; j < 32; ++j) ssum += j < n_cols ? lt_ex2(fmaf(v[j], LT_LOG2E, -mb)) : 0.0f;
                     ls.part[(size_t)(nt * 4 + cq) * ls.Mpad + grow] = make_float2(m, n_cols > 0 ? ssum : 0.0f);
                     if (__any_sync(0xffffffffu, tj >= 0 && tj < n_cols)) {
+                        // select chain in PTX: written in C++ the compiler turns it into v[tj], a dynamically indexed read
+                        // that puts all of v[] in local memory -- 8 x STL.128 per thread and tile in EVERY mode of this
+                        // kernel (64 KB of local stores per tile and SM, as much as the logits themselves)
                         float t = 0.0f;
+                        const int tji = (int)tj;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) t = (j == (int)tj) ? v[j] : t;
+                        for (int j = 0; j < 32; ++j)
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\tselp.f32 %0, %1, %0, p;\n\t}"
+                                         : "+f"(t) : "f"(v[j]), "r"(tji), "r"(j));
                         if (tj >= 0 && tj < n_cols) ls.tgt[grow] = t;
                     }
                 }
