@@ -33,7 +33,9 @@ constexpr int THREADS = 22 * 32;
 constexpr int ROWS_PER_PW = ROWS / N_PROD_WARPS;      // 8
 constexpr int NB = 6;                                 // W^T tiles per row tile: (sv, kb), kb minor
 constexpr int SMEM_A_OFF = 0, SMEM_B_OFF = 2 * A_STAGE, SMEM_BAR_OFF = SMEM_B_OFF + 2 * B_SLOT;
-constexpr int SMEM_BYTES = SMEM_BAR_OFF + 128 + 1024;
+constexpr int STG_LD = 36;                            // padded fp32 row of a scatter warp's [32 rows x 32 columns] staging tile
+constexpr int SMEM_STG_OFF = SMEM_BAR_OFF + 128;
+constexpr int SMEM_BYTES = SMEM_STG_OFF + 4 * 32 * STG_LD * 4 + 1024;
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);   // K-major A and B
 constexpr int IMG_BYTES = NB * B_SLOT;                // 192 KB
 }  // namespace dct
@@ -245,7 +247,14 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
         }
     } else {
         // =============================== SCATTER EPILOGUE ===============================
+        // tcgen05.ld hands every thread 32 columns of ITS row; scattered like that, one warp instruction touches 32
+        // different embedding rows with 16 bytes each (32 half-filled sectors).  Each 32 x 32 chunk therefore goes through
+        // a padded shared-memory tile and leaves as 8 instructions of 4 rows x 128 contiguous bytes (whole sectors, one
+        // cache line per row piece): half as many sector-sized reductions for the L2, an eighth of the lines per request.
         const float inv = wt_hdr[0] / dx_scale;        // exact: both scales are powers of two
+        float *stg = reinterpret_cast<float *>(smem + dct::SMEM_STG_OFF) + warp * (32 * dct::STG_LD);
+        const int wr = lane >> 3, cp = lane & 7;       // writer role: row 4 * it + wr of the warp's 32, 16-byte piece cp of the chunk
+        const int E4 = a.Et / 4;
         for (int tl = 0; tl < my_tiles; ++tl) {
             const long long row = ((long long)blockIdx.x + (long long)tl * gridDim.x) * dct::ROWS + warp * 32 + lane;
             long long is = 0, ip = 0, ie = 0;
@@ -257,7 +266,13 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 #pragma unroll 1
             for (int sv = 0; sv < 3; ++sv) {
                 if (!((sv_mask >> sv) & 1)) continue;
-                float *dst = (sv == 1 ? g_emb_p + (size_t)ip * a.Et : g_emb_t + (size_t)(sv == 0 ? is : ie) * a.Et) + db * dct::E;
+                // start of this lane's row in the table, in 16-byte units (backward_dc_tc_ok: fits 32 bits); ~0 = no row
+                const long long idx = sv == 0 ? is : (sv == 1 ? ip : ie);
+                const uint32_t my_off4 = in_range ? (uint32_t)(idx * E4) : 0xFFFFFFFFu;
+                uint32_t ro[8];
+#pragma unroll
+                for (int it = 0; it < 8; ++it) ro[it] = __shfl_sync(0xffffffffu, my_off4, 4 * it + wr);
+                float4 *tab4 = reinterpret_cast<float4 *>(sv == 1 ? g_emb_p : g_emb_t) + db * (dct::E / 4);
                 mbar_wait(bar_tfull + 8 * sv, (uint32_t)tl & 1u, status);
                 tc_fence_after();
 #pragma unroll 1
@@ -270,14 +285,19 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * sv);
                     }
-                    if (in_range) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float v0 = v[j] * inv, v1 = v[j + 1] * inv, v2 = v[j + 2] * inv, v3 = v[j + 3] * inv;
-                            if (db * dct::E + c * 32 + j < a.Et && (v0 != 0.0f || v1 != 0.0f || v2 != 0.0f || v3 != 0.0f))   // padded contexts: dx == 0
-                                red_add_v4(dst + c * 32 + j, make_float4(v0, v1, v2, v3));
-                        }
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(stg + lane * dct::STG_LD + j) =
+                            make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv);
+                    __syncwarp();
+                    const bool col_ok = db * dct::E + c * 32 + cp * 4 < a.Et;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const float4 w = *reinterpret_cast<const float4 *>(stg + (4 * it + wr) * dct::STG_LD + cp * 4);
+                        if (ro[it] != 0xFFFFFFFFu && col_ok && (w.x != 0.0f || w.y != 0.0f || w.z != 0.0f || w.w != 0.0f))   // padded contexts: dx == 0
+                            red_add_v4(reinterpret_cast<float *>(tab4 + ro[it] + c * 8 + cp), w);
                     }
+                    __syncwarp();                       // the staging tile is rewritten by the next chunk
                 }
             }
         }
@@ -291,7 +311,8 @@ backward_dc_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
 }
 
 bool backward_dc_tc_ok(const EncodeArgs &a) {
-    return a.Et == a.Ep && a.Et <= 2 * dct::E && a.H <= 2 * dct::H && (a.Et & 3) == 0 && (a.H & 3) == 0;
+    return a.Et == a.Ep && a.Et <= 2 * dct::E && a.H <= 2 * dct::H && (a.Et & 3) == 0 && (a.H & 3) == 0 &&
+           (long long)a.T * (a.Et / 4) < 0xFFFFFFFFll && (long long)a.P * (a.Et / 4) < 0xFFFFFFFFll;
 }
 size_t backward_dc_tc_workspace_bytes() { return 1024 + 4 * dct::IMG_BYTES; }      // up to 2 x 2 window pairs
 
