@@ -196,22 +196,30 @@ backward_dw_tc_kernel(const EncodeArgs a, const float *__restrict__ dx, const un
             // thread = row h of dW (TMEM lane); 384 accumulator columns = d; added to the global gradient with 128-bit atomics
             mbar_wait(bar_acc, 0u, status);
             tc_fence_after();
-            const int h = hb * 128 + warp * 32 + lane;
+            // Through a padded shared-memory tile (the operand stages are idle by now), so that one instruction adds 4 rows x
+            // 128 contiguous bytes instead of 16 bytes of 32 different rows (same reason as the scatter of K3c).
             const float inv = 1.0f / dx_scale;
             const int E = a.Et;
-            float *dst = dW + (size_t)h * (3 * E);                 // dW is [H][3E]; accumulator column sv * 128 + (d - 128 db)
+            constexpr int STG_LD = 36;
+            float *stg = reinterpret_cast<float *>(smem + dwt::SMEM_A_OFF) + warp * (32 * STG_LD);
+            const int wr = lane >> 3, cp = lane & 7;
 #pragma unroll 1
             for (int c = 0; c < dwt::D / 32; ++c) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
                 tmem_ld_wait();
-                const int sv = c >> 2, d0 = db * 128 + (c & 3) * 32;
-                if (h < a.H) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (d0 + j < E)
-                            red_add_v4(dst + sv * E + d0 + j, make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv));
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(stg + lane * STG_LD + j) = make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv);
+                __syncwarp();
+                const int sv = c >> 2, d = db * 128 + (c & 3) * 32 + cp * 4;    // accumulator column sv * 128 + (d - 128 db)
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int h = hb * 128 + warp * 32 + 4 * it + wr;
+                    const float4 w = *reinterpret_cast<const float4 *>(stg + (4 * it + wr) * STG_LD + cp * 4);
+                    if (h < a.H && d < E) red_add_v4(dW + (size_t)h * (3 * E) + sv * E + d, w);      // dW is [H][3E]
                 }
+                __syncwarp();
             }
             tc_fence_before();
         }
