@@ -646,4 +646,19 @@ def bind_to_gpu_numa_node(local):
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 during the run (NCCL's
+    # "NCCL version ..." banner at communicator creation) are sent to stderr; print() goes to the real stdout at the end.
+    import io
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = io.StringIO()
+    _py_stdout, sys.stdout = sys.stdout, _buf
+    try:
+        main()
+    finally:
+        sys.stdout = _py_stdout
+        os.dup2(_real_stdout, 1)
+        os.close(_real_stdout)
+        sys.stdout.write(_buf.getvalue())
+        sys.stdout.flush()
