@@ -51,6 +51,7 @@ int launch_label_backward_tc(const c2v_dims *d, const float *cv, const float *G,
                              const float *w_hdr, float *d_cv, float *d_w, float *d_b, unsigned *scratch, cudaStream_t st,
                              bool absmax_ready, const uint8_t *cv_img);
 size_t label_tcgen05_workspace_bytes(const c2v_dims *d, int B);
+bool label_ws_holds_dlogits_of(const void *ws, const float *cv, int B);
 
 // ---- profiling hook (c2v_profile_enable / c2v_profile_read) ----------------------------
 static const int kProfRing = 4096;
@@ -531,7 +532,7 @@ int c2v_label_backward_ws(const c2v_dims *d, const c2v_params *p, const float *c
     if (rc != C2V_OK) return rc;
     // after c2v_label_dlogits on this workspace (the flag's contract: same code_vector, nothing in between) the workspace also
     // holds max |d_outputs| and the fp16 image of code_vector: the backward reads both instead of recomputing them
-    const bool from_dlogits = (algo & C2V_FLAG_GRAD_ABSMAX_READY) != 0;
+    const bool from_dlogits = (algo & C2V_FLAG_GRAD_ABSMAX_READY) != 0 && label_ws_holds_dlogits_of(workspace, code_vector, B);
     return launch_label_backward_tc(d, code_vector, d_outputs, B, img, hdr, d_code_vector, d_output_weight, d_output_bias,
                                     scratch, st, from_dlogits, from_dlogits ? cv_img : nullptr);
 }

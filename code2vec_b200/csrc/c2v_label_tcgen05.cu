@@ -616,6 +616,15 @@ int launch_label_tcgen05(const c2v_dims *d, const float *cv, int B, const float 
     return launch_label_tcgen05_ex(d, cv, B, Wout, bias, out, argmax, maxval, ws, ws_bytes, reuse_prep, st, nullptr);
 }
 
+// What the last label GEMM launched from this host thread left in its workspace: the fp16 image of `cv` (every call) and, in
+// dlogits mode, max |d logit|.  c2v_label_backward_ws only believes C2V_FLAG_GRAD_ABSMAX_READY when this record matches its
+// own workspace / code_vector / B -- a wrong flag then costs the skipped shortcuts, not the result.
+static thread_local struct { const void *ws; const float *cv; int B; bool dlogits; } g_label_last = {nullptr, nullptr, 0, false};
+bool label_ws_holds_dlogits_of(const void *ws, const float *cv, int B)
+{
+    return g_label_last.dlogits && g_label_last.ws == ws && g_label_last.cv == cv && g_label_last.B == B;
+}
+
 // la != NULL: la->loss (mean NLL) / la->lse [B] are produced from the fused partials (out may then be NULL: the logits
 // are never written); la->dlogits_lse != NULL: `out` receives d(loss)/d(logits) instead of the logits.
 int launch_label_tcgen05_ex(const c2v_dims *d, const float *cv, int B, const float *Wout, const float *bias,
@@ -632,6 +641,7 @@ int launch_label_tcgen05_ex(const c2v_dims *d, const float *cv, int B, const flo
         set_error("label workspace too small: %zu < %zu", ws_bytes, label_tcgen05_workspace_bytes(d, B));
         return C2V_EWORKSPACE;
     }
+    g_label_last.ws = ws; g_label_last.cv = cv; g_label_last.B = B; g_label_last.dlogits = la && la->dlogits_lse;
     uint8_t *p = static_cast<uint8_t *>(ws);
     float *hdr = reinterpret_cast<float *>(p);
     unsigned *mxbits = reinterpret_cast<unsigned *>(p + 256);

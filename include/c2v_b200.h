@@ -68,7 +68,9 @@ enum {
 /* OR-ed into `algo` of c2v_label_backward_ws: `d_outputs` is what c2v_label_dlogits wrote with this same workspace for
  * this same `code_vector` and B (and no other call has used the workspace since).  The workspace then already holds
  * max |d_outputs| -- the scale of the fp16 split -- and the fp16 image of code_vector, so the pass over the [B, C] gradient
- * that finds the former and the per-tile conversion of the latter are skipped.  Same results either way. */
+ * that finds the former and the per-tile conversion of the latter are skipped.  Same results either way.  The library
+ * checks the claim against what its last label call on this host thread used (workspace, code_vector, B) and ignores the
+ * flag when they differ. */
 #define C2V_FLAG_GRAD_ABSMAX_READY 0x400
 
 /* Sizes read from the reference's Option (main.py:93-115) by Code2Vec.__init__
