@@ -135,10 +135,14 @@ def test_dlogits_leaves_the_gradient_maximum_for_the_label_backward(B, C, H):
     w_t = cuda(W)
     params = CF.make_params(None, None, None, None, None, None, w_t, cuda(b))
     cache = CF.PrepCache()
-    loss, lse, am, mx, out = CF.label_loss(dims, params, cuda(cv), cuda(lab), cache=cache, weight=w_t)
-    G = CF.label_dlogits(dims, params, cuda(cv), cuda(lab), lse, 1.0 / B, cache=cache, weight=w_t)
-    fast = CF.label_backward(dims, params, cuda(cv), G, cache=cache, weight=w_t, absmax_ready=True)
-    slow = CF.label_backward(dims, params, cuda(cv), G, cache=cache, weight=w_t)
+    cv_d, lab_d = cuda(cv), cuda(lab)       # ONE device tensor: the library honours the flag only for the code_vector pointer dlogits saw
+    loss, lse, am, mx, out = CF.label_loss(dims, params, cv_d, lab_d, cache=cache, weight=w_t)
+    G = CF.label_dlogits(dims, params, cv_d, lab_d, lse, 1.0 / B, cache=cache, weight=w_t)
+    fast = CF.label_backward(dims, params, cv_d, G, cache=cache, weight=w_t, absmax_ready=True)
+    slow = CF.label_backward(dims, params, cv_d, G, cache=cache, weight=w_t)
+    # a different code_vector buffer (same values): the flag is ignored, the result is the same
+    other = CF.label_backward(dims, params, cv_d.clone(), G, cache=cache, weight=w_t, absmax_ready=True)
+    assert torch.equal(other[1], slow[1]) and torch.equal(other[2], slow[2])
     # d_w / d_b: one CTA owns a label tile (deterministic) -> identical bits; d_cv is a split-K sum through atomics
     assert torch.equal(fast[1], slow[1]) and torch.equal(fast[2], slow[2])
     assert (fast[0] - slow[0]).abs().max().item() <= 1e-6 * slow[0].abs().max().item()
